@@ -1,0 +1,469 @@
+"""Tier B oracle: vectorised NumPy restatement of the reference's box-level hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Never imported by the product.
+
+Every function cites the reference lines it restates (paths relative to
+/root/reference).  Arithmetic is float32, one rounding per reference op, in the
+reference's op order (TF's Eigen CPU kernels never contract a*b+c into an FMA).
+
+Pinning status: checked bit-for-bit (masks, indices, labels, matched boxes, keep
+sets) and to <=1 ulp (exp/log outputs) against Tier A = the UNMODIFIED reference
+sources executed over `oracle/tf_shim` (tests/test_oracle_golden.py against the
+committed fixtures in tests/golden/, and live in tests/test_oracle_vs_reference.py
+when /root/reference is present).  The reference has no tests or golden vectors
+of its own, and `tf.nn.top_k`, `tf.argmax`, `tf.image.non_max_suppression`,
+`tf.exp`, `tf.log` live in TensorFlow (absent, version unpinned): for those five
+the adopted semantics are the documented ones written out in oracle/tf_shim.
+
+exp / log policy: the oracle evaluates them as float32(round(f64 libm)), i.e. the
+correctly rounded float32 result (up to double rounding, p ~ 2^-29).  TF/Eigen and
+NumPy's float32 kernels are within 1 ulp of that; the CUDA path computes the same
+double-precision form so masks that depend on decoded boxes stay bit-stable.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+f32 = np.float32
+
+# config.py:15-16,79-80,87
+NORMAL_ANCHOR_RANGE = (0.05, 0.7)
+SPECIAL_ANCHOR_RANGE = (0.02, 0.03)
+REFINE_POS_JAC = (0.2, 0.3, 0.4, 0.4, 0.3, 0.3)
+DET_POS_JAC = (0.5, 0.6, 0.7, 0.7, 0.6, 0.6)
+TOTAL_OBJ_N = 11
+FEAT_SIZES_418 = ((53, 53), (27, 27), (14, 14), (7, 7), (4, 4), (2, 2))   # config.py:34-35
+FEAT_SIZES_512 = ((64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (2, 2))
+
+
+# --------------------------------------------------------------------------- #
+# a1-a4  anchors  (utils/net_tools.py:21-142)
+# --------------------------------------------------------------------------- #
+def init_anchor(n_layers, img_size, normal_range=NORMAL_ANCHOR_RANGE,
+                special_range=SPECIAL_ANCHOR_RANGE):
+    """utils/net_tools.py:21-82 — pixel [h, w] per anchor, float64."""
+    boxes = OrderedDict()
+    amin, amax = normal_range
+    per = (amax - amin) / (n_layers - 1)
+    rmin = amin
+    rmax = rmin + per
+    h, w = img_size
+    s3 = math.sqrt(3)
+    for i in range(n_layers):
+        if i == 0:
+            scales = [special_range[0], special_range[1]]
+        else:
+            scales = [rmin, (2 * rmin + rmax) / 3, (rmin + 2 * rmax) / 3]
+            rmin = rmax
+            rmax = rmin + per
+        rows = []
+        for s in scales:
+            rows += [[s * h, s * w], [s * h / s3, s * w * s3], [s * h * s3, s * w / s3]]
+        a = np.array(rows)
+        a[:, 0] = np.minimum(a[:, 0], h)
+        a[:, 1] = np.minimum(a[:, 1], w)
+        boxes["layer_%d" % (i + 1)] = a
+    return boxes
+
+
+def anchors_one_layer(img_shape, feat_shape, sizes_px, dtype=np.float32):
+    """utils/net_tools.py:98-122 — float64 math, then astype(float32)."""
+    y, x = np.mgrid[0:feat_shape[0], 0:feat_shape[1]]
+    xc = (x + 0.5) / feat_shape[1]
+    yc = (y + 0.5) / feat_shape[0]
+    hh = sizes_px[:, 0] / img_shape[0]
+    ww = sizes_px[:, 1] / img_shape[1]
+    return (np.expand_dims(yc, -1).astype(dtype), np.expand_dims(xc, -1).astype(dtype),
+            hh.astype(dtype), ww.astype(dtype))
+
+
+def anchors_all_layer(img_shape, feat_sizes, anchor_sizes=None):
+    """utils/net_tools.py:125-142 — list over layers of [y, x, h, w]."""
+    if anchor_sizes is None:
+        anchor_sizes = init_anchor(len(feat_sizes), img_shape)
+    out = []
+    for i, (key, val) in enumerate(anchor_sizes.items()):
+        fs = feat_sizes[key] if isinstance(feat_sizes, dict) else feat_sizes[i]
+        out.append(list(anchors_one_layer(img_shape, fs, val)))
+    return out
+
+
+class AnchorTable:
+    """Flat, layer-major then (fy, fx, a) row-major view of the anchors
+    (flatten order of utils/net_tools.py:200,220-223,679-682,731-735)."""
+
+    def __init__(self, anchors_all):
+        corners, centers, shapes = [], [], []
+        for y, x, h, w in anchors_all:
+            y, x, h, w = (np.asarray(v, dtype=f32) for v in (y, x, h, w))
+            # corner form, utils/net_tools.py:156-165 / 203-211 / 385-394 (f32)
+            ymin = y - h / f32(2.)
+            xmin = x - w / f32(2.)
+            ymax = y + h / f32(2.)
+            xmax = x + w / f32(2.)
+            # re-derived centre form, utils/net_tools.py:168-171 / 214-217
+            acy = (ymax + ymin) / f32(2.)
+            acx = (xmax + xmin) / f32(2.)
+            ah = ymax - ymin
+            aw = xmax - xmin
+            corners.append(np.stack([ymin, xmin, ymax, xmax], -1).reshape(-1, 4))
+            centers.append(np.stack([acy, acx, ah, aw], -1).reshape(-1, 4))
+            shapes.append((y.shape[0], y.shape[1], h.shape[0]))
+        self.shapes = shapes                               # (fh, fw, A) per layer
+        self.counts = [s[0] * s[1] * s[2] for s in shapes]
+        self.offsets = np.concatenate([[0], np.cumsum(self.counts)]).astype(np.int64)
+        self.n = int(self.offsets[-1])
+        self.corner = np.concatenate(corners).astype(f32)  # [N,4] ymin,xmin,ymax,xmax
+        self.center = np.concatenate(centers).astype(f32)  # [N,4] acy,acx,ah,aw
+        self.layer_of = np.repeat(np.arange(len(shapes)), self.counts).astype(np.int32)
+
+    def split(self, flat, tail=()):
+        """[..., N, *tail] -> list of [..., fh, fw, A, *tail] per layer."""
+        out = []
+        lead = flat.shape[:flat.ndim - 1 - len(tail)]
+        for l, (fh, fw, a) in enumerate(self.shapes):
+            sl = flat[..., self.offsets[l]:self.offsets[l + 1], :] if tail else \
+                flat[..., self.offsets[l]:self.offsets[l + 1]]
+            out.append(sl.reshape(lead + (fh, fw, a) + tuple(tail)))
+        return out
+
+    @staticmethod
+    def flatten(per_layer, tail_dims):
+        """list of [(B,) fh, fw, A, *tail] -> [(B,) N, *tail] (tail_dims = len(tail))."""
+        outs = []
+        for t in per_layer:
+            t = np.asarray(t)
+            lead = t.ndim - 3 - tail_dims
+            outs.append(t.reshape(t.shape[:lead] + (-1,) + t.shape[t.ndim - tail_dims:]
+                                  if tail_dims else t.shape[:lead] + (-1,)))
+        return np.concatenate(outs, axis=outs[0].ndim - 1 - tail_dims)
+
+
+# --------------------------------------------------------------------------- #
+# a5  box format helpers  (utils/common_tools.py:16-57)
+# --------------------------------------------------------------------------- #
+def center_to_corner(cb):
+    cb = np.asarray(cb, dtype=f32)
+    cy, cx, h, w = cb[..., 0], cb[..., 1], cb[..., 2], cb[..., 3]
+    return np.stack([cy - h / f32(2), cx - w / f32(2), cy + h / f32(2), cx + w / f32(2)], -1)
+
+
+def corner_to_center(cr):
+    cr = np.asarray(cr, dtype=f32)
+    ymin, xmin, ymax, xmax = cr[..., 0], cr[..., 1], cr[..., 2], cr[..., 3]
+    return np.stack([(ymin + ymax) / f32(2.), (xmin + xmax) / f32(2.), ymax - ymin, xmax - xmin], -1)
+
+
+def _exp32(x):
+    with np.errstate(all="ignore"):
+        return np.exp(np.asarray(x, dtype=np.float64)).astype(f32)
+
+
+def _log32(x):
+    with np.errstate(all="ignore"):
+        return np.log(np.asarray(x, dtype=np.float64)).astype(f32)
+
+
+# --------------------------------------------------------------------------- #
+# a6-a8  encode / decode / jaccard  (utils/net_tools.py:147-267)
+# --------------------------------------------------------------------------- #
+def encode(center_anchor, center_bbox):
+    """utils/net_tools.py:173-178 with the re-derived anchor centre form."""
+    a = np.asarray(center_anchor, dtype=f32)
+    g = np.asarray(center_bbox, dtype=f32)
+    with np.errstate(all="ignore"):
+        t_cy = (g[..., 0] - a[..., 0]) / a[..., 2]
+        t_cx = (g[..., 1] - a[..., 1]) / a[..., 3]
+        t_h = _log32(g[..., 2] / a[..., 2])
+        t_w = _log32(g[..., 3] / a[..., 3])
+    return np.stack([t_cy, t_cx, t_h, t_w], -1).astype(f32)
+
+
+def decode(center_anchor, offsets):
+    """utils/net_tools.py:226-231: cy = o0*ah + acy (mul, then add), h = exp(o2)*ah."""
+    a = np.asarray(center_anchor, dtype=f32)
+    o = np.asarray(offsets, dtype=f32)
+    with np.errstate(all="ignore"):
+        cy = o[..., 0] * a[..., 2] + a[..., 0]
+        cx = o[..., 1] * a[..., 3] + a[..., 1]
+        h = _exp32(o[..., 2]) * a[..., 2]
+        w = _exp32(o[..., 3]) * a[..., 3]
+    return np.stack([cy, cx, h, w], -1).astype(f32)
+
+
+def jaccard(anchors_corner, corner_bbox):
+    """utils/net_tools.py:254-266 — plain divide; union = (vol_a - inter) + area_g."""
+    a = np.asarray(anchors_corner, dtype=f32)
+    g = np.asarray(corner_bbox, dtype=f32)
+    with np.errstate(all="ignore"):
+        vol_a = (a[..., 3] - a[..., 1]) * (a[..., 2] - a[..., 0])
+        iymin = np.maximum(a[..., 0], g[..., 0])
+        ixmin = np.maximum(a[..., 1], g[..., 1])
+        iymax = np.minimum(a[..., 2], g[..., 2])
+        ixmax = np.minimum(a[..., 3], g[..., 3])
+        h = np.maximum(iymax - iymin, f32(0.))
+        w = np.maximum(ixmax - ixmin, f32(0.))
+        inter = h * w
+        union = vol_a - inter + (g[..., 2] - g[..., 0]) * (g[..., 3] - g[..., 1])
+        return (inter / union).astype(f32)
+
+
+# --------------------------------------------------------------------------- #
+# a9  ARM matching + encode  (utils/net_tools.py:270-428)
+# --------------------------------------------------------------------------- #
+def arm_match_encode(table, center_bboxes, labels, thresholds=REFINE_POS_JAC,
+                     method="JACCARD_BIGGER"):
+    """One image.  Returns flat (gt[N,4] f32, cbboxes[N,4] f32, labels[N] i32,
+    pos[N] i32, idx[N] i32).  JACCARD_BIGGER: utils/net_tools.py:382-421,316-343;
+    NEAREST_NEIGHBOR: :354-380,283-312."""
+    cb = np.asarray(center_bboxes, dtype=f32).reshape(-1, 4)
+    lab = np.asarray(labels).astype(np.int32)          # :342 cast int64 -> int32
+    g = cb.shape[0]
+    assert g >= 1, "reference crashes on zero GT boxes (utils/net_tools.py:398)"
+    n = table.n
+    if method == "JACCARD_BIGGER":
+        gcorner = center_to_corner(cb)                   # :323,398 (round trip)
+        jac = jaccard(table.corner[None, :, :], gcorner[:, None, :])    # [G,N]
+        best = jac.max(axis=0)                           # :405
+        idx = jac.argmax(axis=0).astype(np.int32)        # :408 first max
+        thr = np.asarray(thresholds, dtype=f32)[table.layer_of]
+        pos = (best >= thr)                              # :406
+    elif method == "NEAREST_NEIGHBOR":
+        enc_all = encode(table.center[None, :, :], cb[:, None, :])      # [G,N,4]
+        with np.errstate(all="ignore"):
+            sq = enc_all * enc_all
+            # tf.reduce_sum over the last axis of 4: Eigen sums sequentially
+            dist = ((sq[..., 0] + sq[..., 1]) + sq[..., 2]) + sq[..., 3]
+        idx = dist.argmin(axis=0).astype(np.int32)       # :365 first min
+        pos = np.ones(n, dtype=bool)                     # :376
+    elif method == "JACCARD_TOPK":
+        raise ValueError("Not support now")              # :424
+    else:
+        raise ValueError('Function parameter "method" wrong')
+    mg = cb[idx]                                         # matched GT centre box
+    enc = encode(table.center, mg)
+    posf = pos[:, None]
+    gt = np.where(posf, enc, f32(0)).astype(f32)
+    cbo = np.where(posf, mg, f32(0)).astype(f32)
+    labo = np.where(pos, lab[idx], 0).astype(np.int32)
+    return gt, cbo, labo, pos.astype(np.int32), idx
+
+
+# --------------------------------------------------------------------------- #
+# a10  ODM target generation  (utils/net_tools.py:431-475)
+# --------------------------------------------------------------------------- #
+def odm_target(table, refine_out, offset_gt, cbboxes, refine_labels, refine_pos,
+               thresholds=DET_POS_JAC):
+    """Flat batched inputs [B,N,4]/[B,N].  Returns (det_gt[B,N,4] f32, mask[B,N]
+    i32, det_labels[B,N] i32, iou[B,N] f32)."""
+    ro = np.asarray(refine_out, dtype=f32)
+    og = np.asarray(offset_gt, dtype=f32)
+    cb = np.asarray(cbboxes, dtype=f32)
+    lab = np.asarray(refine_labels, dtype=np.int32)
+    pm = np.asarray(refine_pos, dtype=np.int32)
+    ref_corner = center_to_corner(decode(table.center, ro))      # :459-460
+    gt_corner = center_to_corner(cb)                              # :463
+    iou = jaccard(ref_corner, gt_corner)                          # :465 elementwise
+    thr = np.asarray(thresholds, dtype=f32)[table.layer_of]
+    with np.errstate(all="ignore"):
+        m = (iou >= thr).astype(np.int32) * pm                    # :468-469
+        det_gt = (og - ro) * m.astype(f32)[..., None]             # :471
+    return det_gt.astype(f32), m, lab * m, iou
+
+
+# --------------------------------------------------------------------------- #
+# a17  inference decode call site  (evaluate.py:139-143, predict.py:130-134)
+# --------------------------------------------------------------------------- #
+def decode_corner(table, refine_out, det_out):
+    s = np.asarray(refine_out, dtype=f32) + np.asarray(det_out, dtype=f32)
+    return center_to_corner(decode(table.center, s))
+
+
+# --------------------------------------------------------------------------- #
+# a11  select  (utils/net_tools.py:658-736)
+# --------------------------------------------------------------------------- #
+def bboxes_select(probs, boxes, select_threshold=None, num_classes=TOTAL_OBJ_N,
+                  ignore_class=0):
+    """probs [B,N,C], boxes [B,N,4] -> dicts c -> [B,N], c -> [B,N,4]."""
+    thr = 0.0 if select_threshold is None else select_threshold
+    p = np.asarray(probs, dtype=f32)
+    b = np.asarray(boxes, dtype=f32)
+    d_s, d_b = {}, {}
+    for c in range(num_classes):
+        if c == ignore_class:
+            continue
+        sc = p[:, :, c]
+        fmask = (sc >= f32(thr)).astype(f32)
+        d_s[c] = sc * fmask
+        d_b[c] = b * fmask[..., None]
+    return d_s, d_b
+
+
+# --------------------------------------------------------------------------- #
+# a12  sort / top-k  (utils/tf_extended/bboxes.py:60-100)
+# --------------------------------------------------------------------------- #
+def topk_indices(scores, k):
+    """tf.nn.top_k: descending, equal values -> lower index first."""
+    s = np.asarray(scores, dtype=f32)
+    assert k <= s.shape[-1], "top_k: k must be <= N"
+    with np.errstate(all="ignore"):
+        return np.argsort(-s, axis=-1, kind="stable")[..., :k].astype(np.int32)
+
+
+def bboxes_sort(scores, bboxes, top_k=400):
+    if isinstance(scores, dict):
+        out = {c: bboxes_sort(scores[c], bboxes[c], top_k) for c in scores}
+        return {c: v[0] for c, v in out.items()}, {c: v[1] for c, v in out.items()}
+    idx = topk_indices(scores, top_k)
+    s = np.take_along_axis(np.asarray(scores, dtype=f32), idx, axis=-1)
+    b = np.take_along_axis(np.asarray(bboxes, dtype=f32), idx[..., None], axis=-2)
+    return s, b
+
+
+# --------------------------------------------------------------------------- #
+# a13  NMS  (utils/tf_extended/bboxes.py:166-232, tensors.py:59-86; TF kernel
+#      semantics per SURVEY.md §8c / oracle/tf_shim)
+# --------------------------------------------------------------------------- #
+def nms_iou_matrix(b):
+    b = np.asarray(b, dtype=f32)
+    ymin = np.minimum(b[:, 0], b[:, 2]); ymax = np.maximum(b[:, 0], b[:, 2])
+    xmin = np.minimum(b[:, 1], b[:, 3]); xmax = np.maximum(b[:, 1], b[:, 3])
+    with np.errstate(all="ignore"):
+        area = (ymax - ymin) * (xmax - xmin)
+        ih = np.maximum(np.minimum(ymax[:, None], ymax[None, :]) -
+                        np.maximum(ymin[:, None], ymin[None, :]), f32(0))
+        iw = np.maximum(np.minimum(xmax[:, None], xmax[None, :]) -
+                        np.maximum(xmin[:, None], xmin[None, :]), f32(0))
+        inter = ih * iw
+        iou = inter / ((area[:, None] + area[None, :]) - inter)
+    bad = (area[:, None] <= 0) | (area[None, :] <= 0)
+    return np.where(bad, f32(0), iou).astype(f32)
+
+
+def nms_indices(scores, bboxes, nms_threshold=0.5, keep_top_k=200):
+    """Indices (selection order) kept by tf.image.non_max_suppression."""
+    s = np.asarray(scores, dtype=f32)
+    with np.errstate(all="ignore"):
+        order = np.argsort(-s, kind="stable")
+    b = np.asarray(bboxes, dtype=f32)[order]
+    over = nms_iou_matrix(b) > f32(nms_threshold)
+    n = len(order)
+    dead = np.zeros(n, dtype=bool)
+    sel = []
+    for i in range(n):
+        if len(sel) >= keep_top_k:
+            break
+        if dead[i]:
+            continue
+        sel.append(i)
+        dead |= over[i]
+    return order[np.asarray(sel, dtype=np.int64)].astype(np.int32)
+
+
+def bboxes_nms(scores, bboxes, nms_threshold=0.5, keep_top_k=200):
+    idx = nms_indices(scores, bboxes, nms_threshold, keep_top_k)
+    s = np.zeros(max(keep_top_k, len(idx)), dtype=f32)
+    b = np.zeros((max(keep_top_k, len(idx)), 4), dtype=f32)
+    s[:len(idx)] = np.asarray(scores, dtype=f32)[idx]
+    b[:len(idx)] = np.asarray(bboxes, dtype=f32)[idx]
+    return s, b
+
+
+def bboxes_nms_batch(scores, bboxes, nms_threshold=0.5, keep_top_k=200):
+    if isinstance(scores, dict):
+        out = {c: bboxes_nms_batch(scores[c], bboxes[c], nms_threshold, keep_top_k)
+               for c in scores}
+        return {c: v[0] for c, v in out.items()}, {c: v[1] for c, v in out.items()}
+    rs, rb = [], []
+    for i in range(len(scores)):
+        s, b = bboxes_nms(scores[i], bboxes[i], nms_threshold, keep_top_k)
+        rs.append(s); rb.append(b)
+    return np.stack(rs), np.stack(rb)
+
+
+# --------------------------------------------------------------------------- #
+# a14, a16  clip / resize / jaccard / intersection  (utils/tf_extended/bboxes.py)
+# --------------------------------------------------------------------------- #
+def bboxes_clip(bbox_ref, bboxes):
+    """utils/tf_extended/bboxes.py:103-136."""
+    if isinstance(bboxes, dict):
+        return {c: bboxes_clip(bbox_ref, v) for c, v in bboxes.items()}
+    r = np.asarray(bbox_ref, dtype=f32)
+    b = np.asarray(bboxes, dtype=f32)
+    ymin = np.maximum(b[..., 0], r[..., 0]); xmin = np.maximum(b[..., 1], r[..., 1])
+    ymax = np.minimum(b[..., 2], r[..., 2]); xmax = np.minimum(b[..., 3], r[..., 3])
+    ymin = np.minimum(ymin, ymax); xmin = np.minimum(xmin, xmax)
+    return np.stack([ymin, xmin, ymax, xmax], -1)
+
+
+def bboxes_resize(bbox_ref, bboxes):
+    """utils/tf_extended/bboxes.py:139-163."""
+    if isinstance(bboxes, dict):
+        return {c: bboxes_resize(bbox_ref, v) for c, v in bboxes.items()}
+    r = np.asarray(bbox_ref, dtype=f32)
+    b = np.asarray(bboxes, dtype=f32)
+    v = np.stack([r[0], r[1], r[0], r[1]])
+    s = np.stack([r[2] - r[0], r[3] - r[1], r[2] - r[0], r[3] - r[1]])
+    with np.errstate(all="ignore"):
+        return ((b - v) / s).astype(f32)
+
+
+def _safe_divide(num, den):
+    """utils/tf_extended/math.py:25-38."""
+    with np.errstate(all="ignore"):
+        return np.where(den > 0, num / den, np.zeros_like(num)).astype(f32)
+
+
+def bboxes_jaccard(bbox_ref, bboxes):
+    """utils/tf_extended/bboxes.py:452-479 — union = ((-inter) + area_b) + area_ref."""
+    r = np.asarray(bbox_ref, dtype=f32)
+    b = np.asarray(bboxes, dtype=f32)
+    iymin = np.maximum(b[..., 0], r[..., 0]); ixmin = np.maximum(b[..., 1], r[..., 1])
+    iymax = np.minimum(b[..., 2], r[..., 2]); ixmax = np.minimum(b[..., 3], r[..., 3])
+    h = np.maximum(iymax - iymin, f32(0)); w = np.maximum(ixmax - ixmin, f32(0))
+    inter = h * w
+    union = (-inter + (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+             + (r[..., 2] - r[..., 0]) * (r[..., 3] - r[..., 1]))
+    return _safe_divide(inter, union)
+
+
+def bboxes_intersection(bbox_ref, bboxes):
+    """utils/tf_extended/bboxes.py:482-508."""
+    r = np.asarray(bbox_ref, dtype=f32)
+    b = np.asarray(bboxes, dtype=f32)
+    iymin = np.maximum(b[..., 0], r[..., 0]); ixmin = np.maximum(b[..., 1], r[..., 1])
+    iymax = np.minimum(b[..., 2], r[..., 2]); ixmax = np.minimum(b[..., 3], r[..., 3])
+    h = np.maximum(iymax - iymin, f32(0)); w = np.maximum(ixmax - ixmin, f32(0))
+    inter = h * w
+    vol = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+    return _safe_divide(inter, vol)
+
+
+# --------------------------------------------------------------------------- #
+# a15  post-process driver  (utils/net_tools.py:739-758)
+# --------------------------------------------------------------------------- #
+def detected_bboxes(probs, boxes, select_threshold=None, nms_threshold=0.5,
+                    clipping_bbox=None, top_k=800, keep_top_k=200,
+                    num_classes=TOTAL_OBJ_N):
+    """probs [B,N,C] (post-softmax), boxes [B,N,4] corner ->
+    dicts c -> [B,keep], c -> [B,keep,4].
+
+    Equivalent compacting evaluation is NOT used here: this
+    is the literal select -> top_k -> NMS -> pad chain, so zero-score entries are
+    real candidates exactly as in the reference."""
+    d_s, d_b = bboxes_select(probs, boxes, select_threshold, num_classes)
+    d_s, d_b = bboxes_sort(d_s, d_b, top_k=top_k)
+    d_s, d_b = bboxes_nms_batch(d_s, d_b, nms_threshold, keep_top_k)
+    if clipping_bbox is not None:
+        d_b = bboxes_clip(clipping_bbox, d_b)
+    return d_s, d_b
+
+
+def softmax(logits):
+    """slim.softmax (evaluate.py:136-137) — row max subtracted, float32."""
+    a = np.asarray(logits, dtype=f32)
+    e = np.exp(a - a.max(axis=-1, keepdims=True))
+    return (e / e.sum(axis=-1, keepdims=True)).astype(f32)

@@ -1,0 +1,67 @@
+"""Deterministic synthetic BDD100K-shaped inputs for tests and bench.
+
+Host-side NumPy only; `seed = 1234 + global_image_index` per image so that any
+rank / shard regenerates exactly the images it owns.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BASE_SEED = 1234
+MAX_GT = 100
+
+
+def gt_boxes(image_index: int, max_gt: int = MAX_GT):
+    """(corner[G,4] f32 in [0,1], labels[G] int64), 1 <= G <= max_gt, h,w >= 1e-3."""
+    rng = np.random.default_rng(BASE_SEED + int(image_index))
+    g = int(rng.integers(1, max_gt + 1))
+    out = np.zeros((0, 4), dtype=np.float32)
+    while out.shape[0] < g:
+        m = 2 * (g - out.shape[0]) + 8
+        c = rng.uniform(0.05, 0.95, size=(m, 2))
+        hw = np.exp(rng.uniform(np.log(0.02), np.log(0.6), size=(m, 2)))
+        cr = np.concatenate([c - hw / 2, c + hw / 2], axis=1)
+        cr = np.clip(cr, 0.0, 1.0).astype(np.float32)
+        ok = ((cr[:, 2] - cr[:, 0]) >= 1e-3) & ((cr[:, 3] - cr[:, 1]) >= 1e-3)
+        out = np.concatenate([out, cr[ok]], axis=0)
+    out = out[:g]
+    labels = rng.integers(1, 11, size=g).astype(np.int64)
+    return out, labels
+
+
+def gt_batch(first_image: int, batch: int, max_gt: int = MAX_GT):
+    """Padded corner boxes [B,max_gt,4] f32, labels [B,max_gt] int64, counts [B] i32."""
+    boxes = np.zeros((batch, max_gt, 4), dtype=np.float32)
+    labels = np.zeros((batch, max_gt), dtype=np.int64)
+    counts = np.zeros((batch,), dtype=np.int32)
+    for b in range(batch):
+        cr, lb = gt_boxes(first_image + b, max_gt)
+        boxes[b, :len(cr)] = cr
+        labels[b, :len(cr)] = lb
+        counts[b] = len(cr)
+    return boxes, labels, counts
+
+
+def head_offsets(image_index: int, n_anchors: int, salt: int = 0, sigma_c=0.1, sigma_s=0.2):
+    """ARM / ODM head output for one image: [N,4] f32 ~ N(0, [sc,sc,ss,ss])."""
+    rng = np.random.default_rng([BASE_SEED + int(image_index), 7919 + salt])
+    o = rng.standard_normal(size=(n_anchors, 4)).astype(np.float32)
+    o[:, :2] *= np.float32(sigma_c)
+    o[:, 2:] *= np.float32(sigma_s)
+    return o
+
+
+def class_probs(image_index: int, n_anchors: int, n_cols: int = 11):
+    """Post-softmax scores [N,11] f32: logits 3*N(0,1) with +4 on background."""
+    rng = np.random.default_rng([BASE_SEED + int(image_index), 104729])
+    z = (rng.standard_normal(size=(n_anchors, n_cols)) * 3.0).astype(np.float32)
+    z[:, 0] += np.float32(4.0)
+    z -= z.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
+
+
+def stress_probs(image_index: int, n_anchors: int, thr: float = 0.3, n_cols: int = 11):
+    """NMS stress (BASELINE config 5): every (anchor, class) score ~ U(thr, 1)."""
+    rng = np.random.default_rng([BASE_SEED + int(image_index), 1299709])
+    return rng.uniform(thr, 1.0, size=(n_anchors, n_cols)).astype(np.float32)

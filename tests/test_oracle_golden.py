@@ -1,0 +1,193 @@
+"""Tier B (oracle/restated.py) against the fixtures produced by running the
+UNMODIFIED reference over the TF shim (oracle/gen_golden.py).  CPU only.
+
+Bar: integer outputs (pos masks, labels, argmax index), matched boxes and NMS keep
+sets bit-exact; exp/log-dependent floats within 1e-5 relative (abs floor 1e-6)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import LAYOUTS, golden, golden_anchors, golden_files
+from oracle import restated as R
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _digest(a):
+    a = np.ascontiguousarray(a)
+    h = hashlib.sha256()
+    h.update(str(a.dtype).encode()); h.update(str(a.shape).encode()); h.update(a.tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("layout", ["418", "512", "tiny"])
+def test_anchor_generation_bit_exact(layout):
+    img, feats = LAYOUTS[layout]
+    ours = R.anchors_all_layer(img, feats)
+    ref = golden_anchors(layout)
+    for (y, x, h, w), (ry, rx, rh, rw) in zip(ours, ref):
+        for a, b in ((y, ry), (x, rx), (h, rh), (w, rw)):
+            assert a.dtype == np.float32 and a.shape == b.shape
+            assert np.array_equal(a, b)
+    z = golden("anchors.npz")
+    sizes = np.concatenate(list(R.init_anchor(6, img).values()))
+    assert np.array_equal(sizes, z["%s_sizes_px" % layout])
+    assert list(z["n_anchor_each_layer"]) == [6, 9, 9, 9, 9, 9]
+
+
+def test_anchor_counts():
+    assert R.AnchorTable(golden_anchors("418")).n == 25800
+    assert R.AnchorTable(golden_anchors("512")).n == 36852
+
+
+def test_box_format():
+    z = golden("box_format.npz")
+    assert np.array_equal(R.corner_to_center(z["corner"]), z["center"])
+    assert np.array_equal(R.center_to_corner(z["center"]), z["corner_back"])
+
+
+@pytest.mark.parametrize("fname", golden_files("targets_"))
+def test_targets(fname):
+    z = golden(fname)
+    layout = str(z["layout"])
+    table = R.AnchorTable(golden_anchors(layout))
+    center, labels = z["center"], z["labels"]
+    assert np.array_equal(R.corner_to_center(z["corner"]), center)
+    gt, cb, lab, pos, idx = R.arm_match_encode(table, center, labels)
+    assert np.array_equal(pos, z["jb_pos"])
+    assert np.array_equal(lab, z["jb_labels"])
+    assert np.array_equal(idx, z["jb_idx"])
+    if "jb_gt" in z:
+        assert np.array_equal(cb, z["jb_cb"])
+        np.testing.assert_allclose(gt, z["jb_gt"], rtol=RTOL, atol=ATOL)
+        ref_gt, ref_cb = z["jb_gt"], z["jb_cb"]
+    else:
+        assert _digest(cb) == str(z["jb_cb_digest"])
+        np.testing.assert_allclose(gt[pos > 0], z["jb_gt_sparse"], rtol=RTOL, atol=ATOL)
+        assert not gt[pos == 0].any()
+        ref_gt = np.zeros_like(gt); ref_gt[pos > 0] = z["jb_gt_sparse"]
+        ref_cb = cb
+    if "nn_gt" in z:
+        ngt, ncb, nlab, npos, _ = R.arm_match_encode(table, center, labels, method="NEAREST_NEIGHBOR")
+        assert np.array_equal(npos, z["nn_pos"]) and np.array_equal(nlab, z["nn_labels"])
+        assert np.array_equal(ncb, z["nn_cb"])
+        np.testing.assert_allclose(ngt, z["nn_gt"], rtol=RTOL, atol=ATOL)
+    if "enc_gt0" in z:
+        np.testing.assert_allclose(R.encode(table.center, center[0]), z["enc_gt0"], rtol=RTOL, atol=ATOL)
+
+    # ODM, fed the REFERENCE's ARM outputs (stage-wise parity)
+    B = z["odm_mask"].shape[0]
+    if "odm_refine_out" in z:
+        ro = z["odm_refine_out"]
+    else:
+        pytest.skip("full-size ODM/decode inputs are regenerated in test_targets_fullsize")
+    og = np.broadcast_to(ref_gt, (B,) + ref_gt.shape)
+    det_gt, m, dl, iou = R.odm_target(table, ro, og, np.broadcast_to(ref_cb, og.shape),
+                                      np.broadcast_to(z["jb_labels"], (B, table.n)),
+                                      np.broadcast_to(z["jb_pos"], (B, table.n)))
+    assert np.array_equal(m, z["odm_mask"])
+    assert np.array_equal(dl, z["odm_labels"])
+    np.testing.assert_allclose(iou, z["odm_iou"], rtol=1e-4, atol=ATOL)
+    assert np.array_equal(det_gt, z["odm_det_gt"])
+    np.testing.assert_allclose(R.decode_corner(table, ro, z["dec_det_out"]), z["dec_corner"],
+                               rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("fname", [f for f in golden_files("targets_r")])
+def test_targets_fullsize(fname):
+    """Full-size fixtures keep only seeds + digests of the random inputs: regenerate
+    them exactly as oracle/gen_golden.py does and check the digests first."""
+    z = golden(fname)
+    layout = str(z["layout"])
+    table = R.AnchorTable(golden_anchors(layout))
+    rng = np.random.default_rng(int(z["seed"]))
+    g = z["corner"].shape[0]
+    rng.uniform(0.1, 0.9, size=(g, 2)); rng.uniform(np.log(0.03), np.log(0.6), size=(g, 2))
+    rng.integers(1, 11, size=g)
+    n, B = table.n, 2
+    gt, cb, lab, pos, _ = R.arm_match_encode(table, z["center"], z["labels"])
+    ref_gt = np.zeros_like(gt); ref_gt[pos > 0] = z["jb_gt_sparse"]
+    ro = (rng.standard_normal(size=(B, n, 4)) * np.array([0.1, 0.1, 0.2, 0.2])).astype(np.float32)
+    ro = np.where(pos[None, :, None] > 0,
+                  (ref_gt[None] + rng.uniform(0, 2.5, size=(B, n, 1)) * ro).astype(np.float32), ro)
+    assert _digest(ro) == str(z["odm_refine_out_digest"]), "fixture inputs could not be regenerated"
+    og = np.broadcast_to(ref_gt, (B, n, 4))
+    det_gt, m, dl, iou = R.odm_target(table, ro, og, np.broadcast_to(cb, og.shape),
+                                      np.broadcast_to(lab, (B, n)), np.broadcast_to(pos, (B, n)))
+    assert np.array_equal(m, z["odm_mask"])
+    assert np.array_equal(dl, z["odm_labels"])
+    np.testing.assert_allclose(iou, z["odm_iou"], rtol=1e-4, atol=ATOL)
+    assert np.array_equal(det_gt[m > 0], z["odm_det_gt_sparse"])
+    do = (rng.standard_normal(size=(B, n, 4)) * np.array([0.1, 0.1, 0.2, 0.2])).astype(np.float32)
+    assert _digest(do) == str(z["dec_det_out_digest"])
+    np.testing.assert_allclose(R.decode_corner(table, ro, do)[:, ::37], z["dec_corner"], rtol=RTOL, atol=ATOL)
+
+
+def _regen_detect_inputs(z, table):
+    rng = np.random.default_rng(int(z["seed"]))
+    B, n = int(z["B"]), table.n
+    mode = str(z["mode"])
+    if mode == "stress":
+        probs = rng.uniform(round(float(z["select_threshold"]), 6), 1.0, size=(B, n, 11)).astype(np.float32)
+        sig = np.array([0.05] * 4)
+    else:
+        zz = (rng.standard_normal(size=(B, n, 11)) * 3.0).astype(np.float32)
+        zz[..., 0] += np.float32(4.0)
+        zz -= zz.max(-1, keepdims=True)
+        e = np.exp(zz)
+        probs = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+        sig = np.array([0.1, 0.1, 0.2, 0.2])
+    ro = (rng.standard_normal(size=(B, n, 4)) * sig).astype(np.float32)
+    do = (rng.standard_normal(size=(B, n, 4)) * sig).astype(np.float32)
+    assert _digest(probs) == str(z["probs_digest"]), "fixture inputs could not be regenerated"
+    assert _digest(ro) == str(z["refine_out_digest"]) and _digest(do) == str(z["det_out_digest"])
+    return probs, ro, do
+
+
+@pytest.mark.parametrize("fname", golden_files("detect_"))
+def test_detected_bboxes(fname):
+    z = golden(fname)
+    layout = str(z["layout"])
+    table = R.AnchorTable(golden_anchors(layout))
+    if "probs" in z:
+        probs, ro, do = z["probs"], z["refine_out"], z["det_out"]
+    else:
+        probs, ro, do = _regen_detect_inputs(z, table)
+    boxes = R.decode_corner(table, ro, do)
+    if "boxes_corner" in z:
+        np.testing.assert_allclose(boxes, z["boxes_corner"], rtol=RTOL, atol=ATOL)
+        boxes = z["boxes_corner"]           # stage-wise: feed the reference's boxes
+    sthr = None if bool(z["select_none"]) else float(z["select_threshold"])
+    clip = z["clip"] if "clip" in z else None
+    rs, rb = R.detected_bboxes(probs, boxes, sthr, float(z["nms_threshold"]), clip,
+                               int(z["top_k"]), int(z["keep_top_k"]))
+    exact = "boxes_corner" in z
+    for c in range(1, 11):
+        if exact:
+            assert np.array_equal(rs[c], z["scores_c%d" % c]), c
+            assert np.array_equal(rb[c], z["bboxes_c%d" % c]), c
+        else:   # boxes come from our own decode (exp within 1 ulp of the reference's)
+            assert np.array_equal(rs[c], z["scores_c%d" % c]), c
+            np.testing.assert_allclose(rb[c], z["bboxes_c%d" % c], rtol=RTOL, atol=ATOL)
+    if "sel_scores_c1" in z:
+        d_s, d_b = R.bboxes_select(probs, boxes, sthr)
+        s_s, s_b = R.bboxes_sort(d_s, d_b, int(z["top_k"]))
+        for c in range(1, 11):
+            assert np.array_equal(d_s[c], z["sel_scores_c%d" % c])
+            assert np.array_equal(d_b[c], z["sel_bboxes_c%d" % c])
+            assert np.array_equal(s_s[c], z["sort_scores_c%d" % c])
+            assert np.array_equal(s_b[c], z["sort_bboxes_c%d" % c])
+
+
+def test_tfe_ops():
+    z = golden("tfe_ops.npz")
+    b, r, s = z["boxes"], z["ref"], z["scores"]
+    assert np.array_equal(R.bboxes_jaccard(r, b), z["jaccard"])
+    assert np.array_equal(R.bboxes_intersection(r, b), z["intersection"])
+    assert np.array_equal(R.bboxes_resize(r, b), z["resize"])
+    assert np.array_equal(R.bboxes_clip(r, b), z["clip"])
+    ns, nb = R.bboxes_nms(s, b, 0.3, 25)
+    assert np.array_equal(ns, z["nms_scores"]) and np.array_equal(nb, z["nms_bboxes"])
+    ss, sb = R.bboxes_sort(s[None], b[None], 20)
+    assert np.array_equal(ss, z["sort_scores"]) and np.array_equal(sb, z["sort_bboxes"])
