@@ -1,0 +1,258 @@
+/*
+ * rodet_b200 — C ABI of the B200-native box-level hot path
+ * (anchor generation, ARM/ODM matching + encoding, decode, select, top-k, NMS)
+ * of the RefineDet-style detector in YoungYoung619/road-object-detection-for-bdd100k.
+ *
+ * The reference has NO native interface for this path: it is ordinary Python that
+ * builds TensorFlow-1 graph ops.  The boundary a maintainer would bind is therefore
+ * the set of Python functions listed below; each entry point cites the reference
+ * function (file:line under /root/reference) it replaces.  INTEGRATION.md shows the
+ * ctypes stub.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  Every data pointer is a DEVICE
+ *    pointer unless the parameter comment says "host".
+ *  - float = IEEE binary32, row-major, innermost dimension contiguous.
+ *  - Boxes are y-first: centre [cy,cx,h,w], corner [ymin,xmin,ymax,xmax], normalised.
+ *  - Anchors are flattened layer-major, then (fy, fx, a) row-major
+ *    (utils/net_tools.py:200,220-223,679-682,731-735).
+ *  - Every function is stream-ordered on `stream` (a cudaStream_t passed as void*),
+ *    never allocates, never synchronises, never reads results back to the host.
+ *  - Return value: 0 on success, a negative ROD_E_* code otherwise; the message is
+ *    available from rod_last_error() (thread-local).
+ *  - There is no CPU fallback anywhere in this library.
+ */
+#ifndef RODET_B200_H_
+#define RODET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROD_ABI_VERSION 1
+#define ROD_MAX_LAYERS 8
+#define ROD_MAX_TOPK 1024          /* top_k / NMS candidates per (image, class) */
+#define ROD_MAX_CLASSES 64
+
+enum {
+  ROD_OK = 0,
+  ROD_E_INVALID = -1,      /* bad argument (null pointer, size, unsupported value) */
+  ROD_E_CUDA = -2,         /* a CUDA runtime call / launch failed */
+  ROD_E_UNSUPPORTED = -3,  /* valid in the reference but not implemented here */
+  ROD_E_DLPACK = -4        /* DLPack tensor on wrong device / dtype / layout */
+};
+
+/* config.refine_method (config.py:74-77) */
+enum { ROD_NEAREST_NEIGHBOR = 0, ROD_JACCARD_BIGGER = 1, ROD_JACCARD_TOPK = 2 };
+
+/* Anchor layout: n_layers feature maps, offset[l]..offset[l+1] is layer l's slice of
+ * the flat anchor axis; offset[n_layers] == n_total. */
+typedef struct rod_layout {
+  int32_t n_layers;
+  int32_t n_total;
+  int32_t offset[ROD_MAX_LAYERS + 1];
+} rod_layout_t;
+
+/* A "list of per-layer tensors" (the reference passes Python lists of 6 tensors of
+ * shape [B, fh, fw, A, inner], nets/catch_net.py:306-308,339-341).  base[l] points at
+ * element (b=0, anchor 0 of layer l); consecutive images are batch_stride[l] ELEMENTS
+ * apart; within an image the layer slice is contiguous. */
+typedef struct rod_layered {
+  const void* base[ROD_MAX_LAYERS];
+  int64_t batch_stride[ROD_MAX_LAYERS];
+} rod_layered_t;
+
+const char* rod_last_error(void);
+int rod_version(void);
+/* host out-params; any may be NULL */
+int rod_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+
+/* ---- a1-a4  anchors ------------------------------------------------------------
+ * Replaces init_anchor / anchors_one_layer / anchors_all_layer
+ * (utils/net_tools.py:21-82, 98-122, 125-142) plus the corner and re-derived centre
+ * forms every consumer recomputes (utils/net_tools.py:156-171, 203-217, 385-394).
+ * feat_h/feat_w/n_anchor: host int32[n_layers]; sizes_px: host double[sum(n_anchor)][2]
+ * = pixel (h, w) per anchor as produced by init_anchor.  Cell centres and normalised
+ * sizes are evaluated in float64 and rounded to float32 exactly like the NumPy code.
+ * Outputs: corner[N,4] (ymin,xmin,ymax,xmax), center[N,4] (acy,acx,ah,aw),
+ * yxhw[N,4] (y,x,h,w as anchors_one_layer returns them; may be NULL). */
+int rod_anchor_table(int n_layers, const int32_t* feat_h, const int32_t* feat_w,
+                     const int32_t* n_anchor, const double* sizes_px, int img_h, int img_w,
+                     float* corner, float* center, float* yxhw, void* stream);
+
+/* Same table from an existing anchors_all_layer() result: y,x = device float[sum fh*fw]
+ * (layer-major, row-major cells), h,w = device float[sum n_anchor]. */
+int rod_anchor_table_from_grid(int n_layers, const int32_t* feat_h, const int32_t* feat_w,
+                               const int32_t* n_anchor, const float* y, const float* x,
+                               const float* h, const float* w, float* corner, float* center,
+                               void* stream);
+
+/* ---- a9  ARM matching + encode ---------------------------------------------------
+ * Replaces refine_groundtruth (utils/net_tools.py:270-428), batched over images (the
+ * reference runs it per image and tf.train.batch stacks, train.py:109-124).
+ * thresholds: host float[n_layers] = config.refine_pos_jac_val_all_layers.
+ * center_bboxes[B,gmax,4], labels[B,gmax] (int64 if labels_i64 else int32),
+ * gt_counts: device int32[B] (NULL => every image has gmax boxes); each count >= 1.
+ * Outputs, flat over the anchor axis: gt[B,N,4], cbboxes[B,N,4], out_labels[B,N],
+ * pos_mask[B,N], match_idx[B,N] (argmax over GT, lowest index on ties; may be NULL).
+ * method ROD_JACCARD_TOPK returns ROD_E_UNSUPPORTED (reference raises
+ * ValueError('Not support now'), utils/net_tools.py:423-424). */
+int rod_arm_match_encode(const rod_layout_t* layout, const float* anchors_corner,
+                         const float* anchors_center, const float* thresholds,
+                         const float* center_bboxes, const void* labels, int labels_i64,
+                         const int32_t* gt_counts, int batch, int gmax, int method,
+                         float* gt, float* cbboxes, int32_t* out_labels, int32_t* pos_mask,
+                         int32_t* match_idx, void* stream);
+
+/* ---- a10  ODM target generation --------------------------------------------------
+ * Replaces det_groundtruth (utils/net_tools.py:431-475).
+ * thresholds: host float[n_layers] = config.det_pos_jac_val_all_layers.
+ * Inputs are per-layer lists: refine_out/offset_gt/cbboxes inner 4 (float),
+ * refine_labels/refine_pos_mask inner 1 (int32).
+ * Outputs flat: det_gt[B,N,4], mask[B,N], det_labels[B,N], iou[B,N]. */
+int rod_odm_target(const rod_layout_t* layout, const float* anchors_center,
+                   const float* thresholds, const rod_layered_t* refine_out,
+                   const rod_layered_t* offset_gt, const rod_layered_t* cbboxes,
+                   const rod_layered_t* refine_labels, const rod_layered_t* refine_pos_mask,
+                   int batch, float* det_gt, int32_t* mask, int32_t* det_labels, float* iou,
+                   void* stream);
+
+/* ---- a7 / a17  decode ------------------------------------------------------------
+ * Replaces decode_locations_one_layer (utils/net_tools.py:182-234) and the inference
+ * call site c2c(decode(anchors, refine_out + det_out)) (evaluate.py:139-143,
+ * predict.py:130-134).  det_out may be NULL (single decode).  to_corner != 0 applies
+ * centerBboxes_2_cornerBboxes.  out flat [B,N,4]. */
+int rod_decode(const rod_layout_t* layout, const float* anchors_center,
+               const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
+               int to_corner, float* out, void* stream);
+
+/* ---- a6  encode one box against every anchor -------------------------------------
+ * Replaces encode_locations_one_layer (utils/net_tools.py:147-179): center_bbox is a
+ * device float[4]; out[n,4] for anchors [first, first+n). */
+int rod_encode_one_box(const float* anchors_center, int first, int n, const float* center_bbox,
+                       float* out, void* stream);
+
+/* ---- a5, a8, a14, a16  element-wise box helpers -----------------------------------
+ * n = number of boxes; every array is [n,4] unless noted.
+ * rod_center_to_corner / rod_corner_to_center: utils/common_tools.py:16-35 / 38-57.
+ * rod_jaccard: net_tools.jaccard (utils/net_tools.py:237-267); b is [n,4] or, when
+ *   b_broadcast != 0, a single box [4]; out[n]; plain divide.
+ * rod_bboxes_jaccard / rod_bboxes_intersection: utils/tf_extended/bboxes.py:452-479 /
+ *   482-508 (safe_divide, utils/tf_extended/math.py:25-38); ref is [4] or [n,4].
+ * rod_bboxes_clip / rod_bboxes_resize: utils/tf_extended/bboxes.py:103-136 / 139-163. */
+int rod_center_to_corner(const float* in, float* out, int64_t n, void* stream);
+int rod_corner_to_center(const float* in, float* out, int64_t n, void* stream);
+int rod_jaccard(const float* a, const float* b, int b_broadcast, float* out, int64_t n,
+                void* stream);
+int rod_bboxes_jaccard(const float* ref, int ref_broadcast, const float* boxes, float* out,
+                       int64_t n, void* stream);
+int rod_bboxes_intersection(const float* ref, int ref_broadcast, const float* boxes,
+                            float* out, int64_t n, void* stream);
+int rod_bboxes_clip(const float* ref, int ref_broadcast, const float* boxes, float* out,
+                    int64_t n, void* stream);
+int rod_bboxes_resize(const float* ref, const float* boxes, float* out, int64_t n,
+                      void* stream);
+
+/* ---- a11  select -----------------------------------------------------------------
+ * Replaces bboxes_select_one_layer / bboxes_select_all_layers
+ * (utils/net_tools.py:658-736): for class c != ignore_class,
+ * scores_c = p_c * (p_c >= thr), bboxes_c = loc * (p_c >= thr).
+ * predictions: per-layer list, inner n_classes; localizations: per-layer list, inner 4.
+ * Outputs class-major: out_scores[n_classes][B][N], out_bboxes[n_classes][B][N][4]
+ * (slot ignore_class is left untouched). */
+int rod_bboxes_select(const rod_layout_t* layout, const rod_layered_t* predictions,
+                      const rod_layered_t* localizations, int batch, int n_classes,
+                      int ignore_class, float select_threshold, float* out_scores,
+                      float* out_bboxes, void* stream);
+
+/* ---- a12  sort / top-k -----------------------------------------------------------
+ * Replaces tfe.bboxes_sort (utils/tf_extended/bboxes.py:60-100): per row of
+ * scores[rows,n] take the top_k largest (descending, equal scores -> lower index
+ * first, TF TopKV2), gather boxes[rows,n,4].  Outputs out_scores[rows,k],
+ * out_bboxes[rows,k,4], out_idx[rows,k] (may be NULL).  1 <= k <= min(n, ROD_MAX_TOPK).
+ * workspace: none. */
+int rod_bboxes_sort(const float* scores, const float* bboxes, int64_t rows, int n, int top_k,
+                    float* out_scores, float* out_bboxes, int32_t* out_idx, void* stream);
+
+/* ---- a13  NMS ---------------------------------------------------------------------
+ * Replaces tfe.bboxes_nms / bboxes_nms_batch (utils/tf_extended/bboxes.py:166-232)
+ * incl. the zero padding of pad_axis (utils/tf_extended/tensors.py:59-86):
+ * greedy tf.image.non_max_suppression over all n candidates of each row (descending
+ * score, ties -> lower index; suppress iff IoU > nms_threshold), outputs in selection
+ * order padded with zeros to keep_top_k.  n <= ROD_MAX_TOPK.
+ * out_scores[rows,keep], out_bboxes[rows,keep,4], out_idx[rows,keep] (-1 padded; may be
+ * NULL). */
+int rod_bboxes_nms_batch(const float* scores, const float* bboxes, int64_t rows, int n,
+                         float nms_threshold, int keep_top_k, float* out_scores,
+                         float* out_bboxes, int32_t* out_idx, void* stream);
+
+/* ---- a15  fused post-process ------------------------------------------------------
+ * Replaces detected_bboxes (utils/net_tools.py:739-758) = select -> top_k -> NMS ->
+ * pad (-> clip), optionally with the decode call site fused in front
+ * (evaluate.py:139-151):
+ *   localizations != NULL : corner boxes are given (drop-in detected_bboxes);
+ *   localizations == NULL : boxes are c2c(decode(anchors_center, refine_out+det_out))
+ *                            evaluated only for the top_k candidates.
+ * clip_box: device float[4] or NULL.  Outputs class-major over classes
+ * c = 0..n_classes-1 (slot ignore_class untouched):
+ *   out_scores[n_classes][B][keep], out_bboxes[n_classes][B][keep][4],
+ *   out_counts[n_classes][B] int32 = number of detections with non-zero score
+ *   (may be NULL; this is what the per-rank NCCL count all-gather ships).
+ * workspace: rod_detect_workspace_bytes(batch, n_classes, top_k) bytes, 256-aligned. */
+size_t rod_detect_workspace_bytes(const rod_layout_t* layout, int batch, int n_classes,
+                                  int top_k);
+int rod_detect(const rod_layout_t* layout, const float* anchors_center,
+               const rod_layered_t* predictions, const rod_layered_t* localizations,
+               const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
+               int n_classes, int ignore_class, float select_threshold, float nms_threshold,
+               int top_k, int keep_top_k, const float* clip_box, float* out_scores,
+               float* out_bboxes, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------
+ * rod_peak_fp32_nofma: runs a dependent-chain FADD/FMUL (no FMA) kernel and returns in
+ * *ops the number of FP32 instructions-lanes issued; time it with events on `stream`. */
+int rod_peak_fp32_nofma(int iters, float* sink, double* ops, void* stream);
+/* rod_l2_flush: writes `bytes` bytes of `buf` (use > L2 size) */
+int rod_l2_flush(void* buf, size_t bytes, void* stream);
+
+/* ---- DLPack front door --------------------------------------------------------------
+ * Same operations, tensors passed as borrowed `DLTensor*` (dlpack.h v0.8 layout; the
+ * Python host hands `DLManagedTensor*` from torch.utils.dlpack.to_dlpack, whose first
+ * member is the DLTensor).  The library never calls the deleter.  Device type, dtype,
+ * rank/shape and contiguity are validated here (ROD_E_DLPACK on mismatch).
+ * Per-layer lists are host arrays of n_layers `DLTensor*`. */
+struct DLTensor;
+int rod_dl_arm_match_encode(const rod_layout_t* layout, const struct DLTensor* anchors_corner,
+                            const struct DLTensor* anchors_center, const float* thresholds,
+                            const struct DLTensor* center_bboxes, const struct DLTensor* labels,
+                            const struct DLTensor* gt_counts, int method,
+                            const struct DLTensor* gt, const struct DLTensor* cbboxes,
+                            const struct DLTensor* out_labels, const struct DLTensor* pos_mask,
+                            const struct DLTensor* match_idx, void* stream);
+int rod_dl_odm_target(const rod_layout_t* layout, const struct DLTensor* anchors_center,
+                      const float* thresholds, const struct DLTensor* const* refine_out,
+                      const struct DLTensor* const* offset_gt, const struct DLTensor* const* cbboxes,
+                      const struct DLTensor* const* refine_labels,
+                      const struct DLTensor* const* refine_pos_mask, const struct DLTensor* det_gt,
+                      const struct DLTensor* mask, const struct DLTensor* det_labels,
+                      const struct DLTensor* iou, void* stream);
+int rod_dl_decode(const rod_layout_t* layout, const struct DLTensor* anchors_center,
+                  const struct DLTensor* const* refine_out, const struct DLTensor* const* det_out,
+                  int to_corner, const struct DLTensor* out, void* stream);
+int rod_dl_detect(const rod_layout_t* layout, const struct DLTensor* anchors_center,
+                  const struct DLTensor* const* predictions,
+                  const struct DLTensor* const* localizations,
+                  const struct DLTensor* const* refine_out, const struct DLTensor* const* det_out,
+                  int ignore_class, float select_threshold, float nms_threshold, int top_k,
+                  int keep_top_k, const struct DLTensor* clip_box, const struct DLTensor* out_scores,
+                  const struct DLTensor* out_bboxes, const struct DLTensor* out_counts,
+                  const struct DLTensor* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RODET_B200_H_ */

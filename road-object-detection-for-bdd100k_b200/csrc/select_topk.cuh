@@ -1,0 +1,38 @@
+// Score sources and the exact segmented top-k used by rod_bboxes_sort and rod_detect.
+#pragma once
+#include "common.cuh"
+
+namespace rod {
+
+// Row r of a dense [rows, n] score matrix (tfe.bboxes_sort on tensors).
+struct DenseScores {
+  const float* scores;
+  int n;
+  __device__ __forceinline__ int size() const { return n; }
+  __device__ __forceinline__ bool row_active(long long) const { return true; }
+  // returns the (masked) score; real == false marks entries whose box was zeroed by select
+  __device__ __forceinline__ float fetch(long long r, int i, bool& real) const {
+    real = true;
+    return __ldg(scores + r * n + i);
+  }
+};
+
+// Fused select (utils/net_tools.py:686-695) over the per-layer prediction list: row r =
+// c * batch + b reads class column c of image b; scores = p * (p >= thr).
+struct SelectedScores {
+  LayeredF probs;
+  Layout L;
+  int n_classes, ignore_class, batch;
+  float thr;
+  __device__ __forceinline__ int size() const { return L.n_total; }
+  __device__ __forceinline__ bool row_active(long long r) const { return (int)(r / batch) != ignore_class; }
+  __device__ __forceinline__ float fetch(long long r, int i, bool& real) const {
+    const int c = (int)(r / batch), b = (int)(r % batch);
+    const int l = layer_of(L, i);
+    const float p = __ldg(probs.base[l] + (long long)b * probs.stride[l] + (long long)(i - L.offset[l]) * n_classes + c);
+    real = p >= thr;
+    return __fmul_rn(p, real ? 1.f : 0.f);
+  }
+};
+
+}  // namespace rod

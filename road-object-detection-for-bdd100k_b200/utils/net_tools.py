@@ -1,0 +1,371 @@
+"""Drop-in for the hot-path functions of the reference's `utils/net_tools.py`
+(anchors :21-142, encode/decode/jaccard :147-267, refine_groundtruth :270-428,
+det_groundtruth :431-475, select :658-736, detected_bboxes :739-758).
+
+Same names, positional/keyword parameters and defaults; CUDA `torch.Tensor`s where the
+reference takes `tf.Tensor`s; the same list-per-layer / dict-per-class return structures.
+`scope=` arguments are accepted and ignored.  Every function runs hand-written sm_100a
+kernels through the C ABI (`include/rodet_b200.h`); nothing falls back to the CPU.
+
+Extensions (not in the reference): `refine_groundtruth` also accepts a batch
+(`center_bboxes[B,Gmax,4]`, `labels[B,Gmax]`, `gt_counts[B]`), since the reference runs it per
+image and lets `tf.train.batch` stack the results (train.py:109-124);
+`decode_detected_bboxes` fuses the decode call site (evaluate.py:139-143) into
+`detected_bboxes`; `return_match_index=True` exposes the internal argmax."""
+from __future__ import annotations
+
+import collections
+import math
+
+import numpy as np
+import torch
+
+from .. import _abi, config
+from ..anchor_table import AnchorTable, layer_table_for, table_for
+
+__all__ = [
+    "init_anchor", "n_anchor_each_layer", "anchors_one_layer", "anchors_all_layer",
+    "encode_locations_one_layer", "decode_locations_one_layer", "jaccard", "refine_groundtruth",
+    "det_groundtruth", "bboxes_select_one_layer", "bboxes_select_all_layers", "detected_bboxes",
+    "decode_detected_bboxes",
+]
+
+
+# --------------------------------------------------------------------------------- anchors
+def init_anchor(n_layers):
+    """Pixel (height, width) of every anchor shape per layer, float64
+    (utils/net_tools.py:21-82).  Reads `config.img_size`, `config.normal_anchor_range` and
+    `config.special_anchor_range` like the reference."""
+    img_h, img_w = config.img_size
+    lo, hi = config.normal_anchor_range
+    step = (hi - lo) / (n_layers - 1)
+    root3 = math.sqrt(3)
+    table = collections.OrderedDict()
+    band_lo, band_hi = lo, lo + step
+    for layer in range(n_layers):
+        if layer == 0:
+            scales = list(config.special_anchor_range)
+        else:
+            scales = [band_lo, (2 * band_lo + band_hi) / 3, (band_lo + 2 * band_hi) / 3]
+            band_lo, band_hi = band_hi, band_hi + step
+        shapes = []
+        for s in scales:                         # ratios 1:1, 1:3 (wide), 3:1 (tall)
+            shapes.append([s * img_h, s * img_w])
+            shapes.append([s * img_h / root3, s * img_w * root3])
+            shapes.append([s * img_h * root3, s * img_w / root3])
+        px = np.array(shapes)
+        px[:, 0] = np.minimum(px[:, 0], img_h)   # clip to the image
+        px[:, 1] = np.minimum(px[:, 1], img_w)
+        table["layer_%d" % (layer + 1)] = px
+    return table
+
+
+def n_anchor_each_layer(backbone_name):
+    """[6, 9, 9, 9, 9, 9] (utils/net_tools.py:84-94)."""
+    assert backbone_name in list(config.extract_feat_name.keys())
+    shapes = init_anchor(len(config.extract_feat_name[backbone_name]))
+    return [v.shape[0] for v in shapes.values()]
+
+
+def anchors_one_layer(img_shape, feat_shape, anchors_one_layer, dtype=np.float32):
+    """Cell centres y[fh,fw,1], x[fh,fw,1] and normalised sizes h[A], w[A]; float64 math,
+    then cast (utils/net_tools.py:98-122).  Host NumPy, as in the reference."""
+    rows, cols = np.mgrid[0:feat_shape[0], 0:feat_shape[1]]
+    yc = ((rows + 0.5) / feat_shape[0])[..., None]
+    xc = ((cols + 0.5) / feat_shape[1])[..., None]
+    hh = anchors_one_layer[:, 0] / img_shape[0]
+    ww = anchors_one_layer[:, 1] / img_shape[1]
+    return yc.astype(dtype), xc.astype(dtype), hh.astype(dtype), ww.astype(dtype)
+
+
+def anchors_all_layer(img_shape, feats_shape, anchors_all_layer):
+    """List over layers of [y, x, h, w] (utils/net_tools.py:125-142)."""
+    out = []
+    for key, px in anchors_all_layer.items():
+        out.append(list(anchors_one_layer(img_shape=img_shape, feat_shape=feats_shape[key],
+                                          anchors_one_layer=px)))
+    return out
+
+
+# --------------------------------------------------------------------------------- helpers
+def _f32(t, name):
+    t = _abi.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s must be float32" % name)
+    return t
+
+
+def _check_list(ts, table, name):
+    if len(ts) != table.n_layers:
+        raise ValueError("%s has %d layers, anchors have %d" % (name, len(ts), table.n_layers))
+    return list(ts)
+
+
+def _thresholds(vals, table, name):
+    vals = list(vals)
+    if len(vals) < table.n_layers:
+        raise ValueError("%s has %d entries for %d layers" % (name, len(vals), table.n_layers))
+    return _abi.float_array(vals[:table.n_layers])
+
+
+# --------------------------------------------------------------------------------- encode / decode / jaccard
+def encode_locations_one_layer(anchors_one_layer, center_bbox):
+    """Offsets of ONE box [y, x, h, w] w.r.t. every anchor of a layer -> [fh, fw, A, 4]
+    (utils/net_tools.py:147-179)."""
+    box = _f32(center_bbox, "center_bbox").reshape(-1)
+    if box.numel() != 4:
+        raise ValueError("center_bbox must have 4 elements")
+    t = layer_table_for(anchors_one_layer, box.device)
+    out = torch.empty((t.n, 4), dtype=torch.float32, device=box.device)
+    box = box.contiguous()
+    with torch.cuda.device(box.device):
+        _abi.check(_abi.lib.rod_encode_one_box(t.center.data_ptr(), 0, t.n, box.data_ptr(), out.data_ptr(),
+                                               _abi.stream_ptr(box.device)))
+    fh, fw, a = t.shapes[0]
+    return out.view(fh, fw, a, 4)
+
+
+def decode_locations_one_layer(anchors_one_layer, offset_bboxes):
+    """Centre boxes [y, x, h, w] from offsets of shape [B, ..., 4] for one layer
+    (utils/net_tools.py:182-234); the result has the input's shape."""
+    off = _f32(offset_bboxes, "offset_bboxes")
+    t = layer_table_for(anchors_one_layer, off.device)
+    if off.dim() < 2 or off.shape[-1] != 4 or off[0].numel() != t.n * 4:
+        raise ValueError("offset_bboxes must be [B, ..., 4] with %d anchors per image" % t.n)
+    return _decode(t, [off], None, to_corner=False).view(off.shape)
+
+
+def _decode(table, refine_out, det_out, to_corner):
+    dev = refine_out[0].device
+    B = refine_out[0].shape[0]
+    out = torch.empty((B, table.n, 4), dtype=torch.float32, device=dev)
+    if B == 0:
+        return out
+    a = _abi.DLArgs()
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib.rod_dl_decode(table.layout, a.one(table.center), a.many(refine_out),
+                                          a.many(det_out), 1 if to_corner else 0, a.one(out),
+                                          _abi.stream_ptr(dev)))
+    return out
+
+
+def jaccard(anchors, corner_bbox):
+    """IoU of corner boxes `anchors[..., 4]` with `corner_bbox` ([4] or the same shape)
+    -> [...]; plain divide, no safe-divide (utils/net_tools.py:237-267)."""
+    a = _f32(anchors, "anchors").contiguous()
+    g = _f32(corner_bbox, "corner_bbox").contiguous()
+    n = a.numel() // 4
+    bc = 1 if g.numel() == 4 and n != 1 else 0
+    if not bc and g.numel() != a.numel():
+        raise ValueError("corner_bbox must have 4 elements or the shape of anchors")
+    out = torch.empty(a.shape[:-1], dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _abi.check(_abi.lib.rod_jaccard(a.data_ptr(), g.data_ptr(), bc, out.data_ptr(), n,
+                                        _abi.stream_ptr(a.device)))
+    return out
+
+
+# --------------------------------------------------------------------------------- a9 ARM
+def refine_groundtruth(anchors_all_layer, center_bboxes, labels, method, scope="refine_encode",
+                       gt_counts=None, return_match_index=False, thresholds=None):
+    """ARM matching + encoding (utils/net_tools.py:270-428).
+
+    Per image (reference form): center_bboxes[G,4], labels[G] -> four lists over layers of
+    gt[fh,fw,A,4], cbboxes[fh,fw,A,4], labels[fh,fw,A,1] (int32), pos_mask[fh,fw,A,1] (int32).
+    Batched extension: center_bboxes[B,Gmax,4], labels[B,Gmax], gt_counts[B] (int32, >= 1) ->
+    the same lists with a leading batch dimension."""
+    if method == config.refine_method.JACCARD_TOPK:
+        raise ValueError('Not support now')                       # :424
+    if method not in (config.refine_method.NEAREST_NEIGHBOR, config.refine_method.JACCARD_BIGGER):
+        raise ValueError('Function parameter "method" wrong')      # :426
+    cb = _f32(center_bboxes, "center_bboxes")
+    lab = _abi.require_cuda(labels, "labels")
+    batched = cb.dim() == 3
+    if not batched:
+        if cb.dim() != 2:
+            raise ValueError("center_bboxes must be [G,4] or [B,Gmax,4]")
+        cb, lab = cb.unsqueeze(0), lab.unsqueeze(0)
+    if cb.shape[-1] != 4 or lab.shape != cb.shape[:2]:
+        raise ValueError("center_bboxes [.., G, 4] and labels [.., G] do not agree")
+    if cb.shape[1] < 1:
+        raise ValueError("at least one ground-truth box per image is required "
+                         "(the reference indexes center_bboxes[0], utils/net_tools.py:398)")
+    if lab.dtype not in (torch.int64, torch.int32):
+        raise ValueError("labels must be int64 or int32")
+    dev = cb.device
+    table = table_for(anchors_all_layer, dev)
+    thr = _thresholds(config.refine_pos_jac_val_all_layers if thresholds is None else thresholds,
+                      table, "refine_pos_jac_val_all_layers")
+    cb, lab = cb.contiguous(), lab.contiguous()
+    if gt_counts is not None:
+        gt_counts = _abi.require_cuda(gt_counts, "gt_counts").to(torch.int32).contiguous()
+    B, N = cb.shape[0], table.n
+    gt = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    cbo = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    lbo = torch.empty((B, N), dtype=torch.int32, device=dev)
+    pos = torch.empty((B, N), dtype=torch.int32, device=dev)
+    idx = torch.empty((B, N), dtype=torch.int32, device=dev) if return_match_index else None
+    a = _abi.DLArgs()
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib.rod_dl_arm_match_encode(
+            table.layout, a.one(table.corner), a.one(table.center), thr, a.one(cb), a.one(lab),
+            a.one(gt_counts), int(method.value), a.one(gt), a.one(cbo), a.one(lbo), a.one(pos), a.one(idx),
+            _abi.stream_ptr(dev)))
+    res = (table.split(gt, batched), table.split(cbo, batched), table.split(lbo, batched, True),
+           table.split(pos, batched, True))
+    if return_match_index:
+        return res + (table.split(idx, batched),)
+    return res
+
+
+# --------------------------------------------------------------------------------- a10 ODM
+def det_groundtruth(refine_out, offset_gt, cbboxes, refine_labels, refine_pos_mask, anchors,
+                    scope="det_encode", thresholds=None):
+    """ODM target generation (utils/net_tools.py:431-475): four lists over layers of
+    det_gt[B,fh,fw,A,4], mask[B,fh,fw,A,1] (int32), det_labels[B,fh,fw,A,1] (int32),
+    iou[B,fh,fw,A]."""
+    dev = _f32(refine_out[0], "refine_out").device
+    table = table_for(anchors, dev)
+    ro = [_f32(t, "refine_out") for t in _check_list(refine_out, table, "refine_out")]
+    og = [_f32(t, "offset_gt") for t in _check_list(offset_gt, table, "offset_gt")]
+    cb = [_f32(t, "cbboxes") for t in _check_list(cbboxes, table, "cbboxes")]
+    lb = [t.to(torch.int32) for t in _check_list(refine_labels, table, "refine_labels")]
+    pm = [t.to(torch.int32) for t in _check_list(refine_pos_mask, table, "refine_pos_mask")]
+    thr = _thresholds(config.det_pos_jac_val_all_layers if thresholds is None else thresholds,
+                      table, "det_pos_jac_val_all_layers")
+    B, N = ro[0].shape[0], table.n
+    det_gt = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, N), dtype=torch.int32, device=dev)
+    dlab = torch.empty((B, N), dtype=torch.int32, device=dev)
+    iou = torch.empty((B, N), dtype=torch.float32, device=dev)
+    if B:
+        a = _abi.DLArgs()
+        with torch.cuda.device(dev):
+            _abi.check(_abi.lib.rod_dl_odm_target(
+                table.layout, a.one(table.center), thr, a.many(ro), a.many(og), a.many(cb), a.many(lb),
+                a.many(pm), a.one(det_gt), a.one(mask), a.one(dlab), a.one(iou), _abi.stream_ptr(dev)))
+    return (table.split(det_gt), table.split(mask, True, True), table.split(dlab, True, True),
+            table.split(iou))
+
+
+# --------------------------------------------------------------------------------- a11 select
+def bboxes_select_one_layer(predictions_layer, localizations_layer, select_threshold=None,
+                            num_classes=21, ignore_class=0, scope=None):
+    """Per class c != ignore_class: scores = p_c * (p_c >= thr), bboxes = loc * (p_c >= thr)
+    -> dicts c -> [B, N_l], c -> [B, N_l, 4] (utils/net_tools.py:658-697)."""
+    return _select([predictions_layer], [localizations_layer], select_threshold, num_classes, ignore_class)
+
+
+def bboxes_select_all_layers(predictions_net, localizations_net, select_threshold=None,
+                             num_classes=21, ignore_class=0, scope=None):
+    """The same over all layers, concatenated on the anchor axis (utils/net_tools.py:700-736)."""
+    return _select(list(predictions_net), list(localizations_net), select_threshold, num_classes, ignore_class)
+
+
+def _layout_from_lists(preds, inner):
+    counts = []
+    for p in preds:
+        if p.dim() < 3 or p[0].numel() % inner:
+            raise ValueError("per-layer tensors must be [B, ..., %d]" % inner)
+        counts.append(p[0].numel() // inner)
+    lay = _abi.Layout()
+    lay.n_layers = len(counts)
+    off = 0
+    for i, c in enumerate(counts):
+        lay.offset[i] = off
+        off += c
+    lay.offset[len(counts)] = off
+    lay.n_total = off
+    return lay, off
+
+
+def _select(preds, locs, select_threshold, num_classes, ignore_class):
+    thr = 0.0 if select_threshold is None else float(select_threshold)
+    preds = [_f32(p, "predictions") for p in preds]
+    locs = [_f32(l, "localizations") for l in locs]
+    if len(preds) != len(locs) or len(preds) > _abi.MAX_LAYERS:
+        raise ValueError("predictions / localizations layer lists do not agree")
+    C = preds[0].shape[-1]
+    if num_classes > C:
+        raise ValueError("num_classes=%d exceeds the prediction depth %d" % (num_classes, C))
+    dev, B = preds[0].device, preds[0].shape[0]
+    lay, N = _layout_from_lists(preds, C)
+    for p, l in zip(preds, locs):
+        if l.shape[-1] != 4 or l[0].numel() // 4 != p[0].numel() // C or l.shape[0] != B:
+            raise ValueError("predictions and localizations do not describe the same anchors")
+    scores = torch.empty((C, B, N), dtype=torch.float32, device=dev)
+    boxes = torch.empty((C, B, N, 4), dtype=torch.float32, device=dev)
+    if B:
+        pl, k1 = _abi.layered(preds, C)
+        ll, k2 = _abi.layered(locs, 4)
+        with torch.cuda.device(dev):
+            _abi.check(_abi.lib.rod_bboxes_select(lay, pl, ll, B, C, ignore_class, thr, scores.data_ptr(),
+                                                  boxes.data_ptr(), _abi.stream_ptr(dev)))
+        del k1, k2
+    d_scores, d_bboxes = {}, {}
+    for c in range(num_classes):
+        if c != ignore_class:
+            d_scores[c] = scores[c]
+            d_bboxes[c] = boxes[c]
+    return d_scores, d_bboxes
+
+
+# --------------------------------------------------------------------------------- a15 post-process
+def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_threshold, clipping_bbox,
+            top_k, keep_top_k, num_classes, return_counts):
+    thr = 0.0 if select_threshold is None else float(select_threshold)
+    preds = [_f32(p, "predictions") for p in preds]
+    dev, B, C = preds[0].device, preds[0].shape[0], preds[0].shape[-1]
+    if num_classes > C:
+        raise ValueError("num_classes=%d exceeds the prediction depth %d" % (num_classes, C))
+    if anchors is not None:
+        table = table_for(anchors, dev)
+        lay, N, center = table.layout, table.n, table.center
+        _check_list(preds, table, "predictions")
+    else:
+        lay, N = _layout_from_lists(preds, C)
+        center = None
+    if top_k > N:
+        raise ValueError("top_k=%d must be <= the number of anchors %d (tf.nn.top_k)" % (top_k, N))
+    scores = torch.empty((C, B, keep_top_k), dtype=torch.float32, device=dev)
+    boxes = torch.empty((C, B, keep_top_k, 4), dtype=torch.float32, device=dev)
+    counts = torch.empty((C, B), dtype=torch.int32, device=dev) if return_counts else None
+    if B:
+        ws = torch.empty((int(_abi.lib.rod_detect_workspace_bytes(lay, B, C, top_k)),), dtype=torch.uint8, device=dev)
+        clip = None
+        if clipping_bbox is not None:
+            clip = torch.as_tensor(clipping_bbox, dtype=torch.float32, device=dev).reshape(4).contiguous()
+        a = _abi.DLArgs()
+        with torch.cuda.device(dev):
+            _abi.check(_abi.lib.rod_dl_detect(
+                lay, a.one(center), a.many(preds), a.many(locs), a.many(refine_out), a.many(det_out), 0, thr,
+                float(nms_threshold), int(top_k), int(keep_top_k), a.one(clip), a.one(scores), a.one(boxes),
+                a.one(counts), a.one(ws), _abi.stream_ptr(dev)))
+    rscores = {c: scores[c] for c in range(1, num_classes)}
+    rbboxes = {c: boxes[c] for c in range(1, num_classes)}
+    if return_counts:
+        return rscores, rbboxes, counts
+    return rscores, rbboxes
+
+
+def detected_bboxes(predictions, localisations, select_threshold=None, nms_threshold=0.5,
+                    clipping_bbox=None, top_k=800, keep_top_k=200, return_counts=False):
+    """select -> top_k -> per-class NMS -> zero-pad (-> clip) in two kernels
+    (utils/net_tools.py:739-758).  predictions: list of [B,fh,fw,A,11] post-softmax scores;
+    localisations: list of [B,fh,fw,A,4] corner boxes.  Returns dicts c -> [B,keep_top_k],
+    c -> [B,keep_top_k,4] for c = 1..config.total_obj_n-1."""
+    locs = [_f32(l, "localisations") for l in localisations]
+    return _detect(list(predictions), locs, None, None, None, select_threshold, nms_threshold,
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts)
+
+
+def decode_detected_bboxes(anchors_all_layer, refine_out, det_out, predictions, select_threshold=None,
+                           nms_threshold=0.5, clipping_bbox=None, top_k=800, keep_top_k=200,
+                           return_counts=False):
+    """Extension: the inference call sequence of evaluate.py:139-151 in one call —
+    c2c(decode(anchors, refine_out + det_out)) is evaluated only for the top_k candidates of
+    each (image, class) instead of materialising [B,N,4] boxes first."""
+    ro = [_f32(t, "refine_out") for t in refine_out]
+    do = [_f32(t, "det_out") for t in det_out]
+    return _detect(list(predictions), None, ro, do, anchors_all_layer, select_threshold, nms_threshold,
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts)

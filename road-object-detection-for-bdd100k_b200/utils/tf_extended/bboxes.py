@@ -1,0 +1,136 @@
+"""Drop-in for the hot-path functions of `utils/tf_extended/bboxes.py`:
+bboxes_sort(:60-100), bboxes_sort_all_classes(:27-57), bboxes_clip(:103-136),
+bboxes_resize(:139-163), bboxes_nms(:166-189), bboxes_nms_batch(:192-232),
+bboxes_jaccard(:452-479), bboxes_intersection(:482-508).
+CUDA torch tensors in, CUDA kernels underneath (include/rodet_b200.h); dict inputs are
+treated per class like the reference does."""
+from __future__ import annotations
+
+import torch
+
+from ... import _abi
+
+__all__ = ["bboxes_sort_all_classes", "bboxes_sort", "bboxes_clip", "bboxes_resize", "bboxes_nms",
+           "bboxes_nms_batch", "bboxes_jaccard", "bboxes_intersection"]
+
+
+def _f32(t, name):
+    t = _abi.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s must be float32" % name)
+    return t.contiguous()
+
+
+def _sort(scores, bboxes, top_k, want_idx):
+    s = _f32(scores, "scores")
+    b = _f32(bboxes, "bboxes")
+    if s.dim() != 2 or b.shape != s.shape + (4,):
+        raise ValueError("bboxes_sort expects scores [B,N] and bboxes [B,N,4]")
+    B, N = s.shape
+    if not 1 <= top_k <= N:
+        raise ValueError("top_k=%d must be in [1, N=%d] (tf.nn.top_k requires k <= N)" % (top_k, N))
+    os_ = torch.empty((B, top_k), dtype=torch.float32, device=s.device)
+    ob = torch.empty((B, top_k, 4), dtype=torch.float32, device=s.device)
+    oi = torch.empty((B, top_k), dtype=torch.int32, device=s.device) if want_idx else None
+    with torch.cuda.device(s.device):
+        _abi.check(_abi.lib.rod_bboxes_sort(s.data_ptr(), b.data_ptr(), B, N, int(top_k), os_.data_ptr(),
+                                            ob.data_ptr(), oi.data_ptr() if want_idx else None,
+                                            _abi.stream_ptr(s.device)))
+    return os_, ob, oi
+
+
+def bboxes_sort_all_classes(classes, scores, bboxes, top_k=400, scope=None):
+    """Sort by decreasing score keeping top_k; classes are gathered alongside."""
+    s, b, idx = _sort(scores, bboxes, top_k, True)
+    return torch.gather(classes, 1, idx.long()), s, b
+
+
+def bboxes_sort(scores, bboxes, top_k=400, scope=None):
+    """tf.nn.top_k(scores, k, sorted=True) + per-image gather of the boxes; equal scores keep
+    the lower index first.  Dicts are processed per class."""
+    if isinstance(scores, dict) or isinstance(bboxes, dict):
+        d_scores, d_bboxes = {}, {}
+        for c in scores.keys():
+            d_scores[c], d_bboxes[c] = bboxes_sort(scores[c], bboxes[c], top_k=top_k)
+        return d_scores, d_bboxes
+    s, b, _ = _sort(scores, bboxes, top_k, False)
+    return s, b
+
+
+def _ref_op(fn, bbox_ref, bboxes, out_inner):
+    b = _f32(bboxes, "bboxes")
+    r = torch.as_tensor(bbox_ref, dtype=torch.float32, device=b.device).contiguous()
+    n = b.numel() // 4
+    if r.numel() == 4:
+        bc = 1
+    elif r.numel() == b.numel():
+        bc = 0
+    else:
+        raise ValueError("bbox_ref must be a single box or match bboxes")
+    out = torch.empty(b.shape if out_inner == 4 else b.shape[:-1], dtype=torch.float32, device=b.device)
+    with torch.cuda.device(b.device):
+        _abi.check(fn(r.data_ptr(), bc, b.data_ptr(), out.data_ptr(), n, _abi.stream_ptr(b.device)))
+    return out
+
+
+def bboxes_clip(bbox_ref, bboxes, scope=None):
+    """Intersect boxes with a reference box; empty boxes collapse (ymin=min(ymin,ymax))."""
+    if isinstance(bboxes, dict):
+        return {c: bboxes_clip(bbox_ref, bboxes[c]) for c in bboxes.keys()}
+    return _ref_op(_abi.lib.rod_bboxes_clip, bbox_ref, bboxes, 4)
+
+
+def bboxes_resize(bbox_ref, bboxes, name=None):
+    """Express boxes in the frame of `bbox_ref` (which maps to [0,0,1,1])."""
+    if isinstance(bboxes, dict):
+        return {c: bboxes_resize(bbox_ref, bboxes[c]) for c in bboxes.keys()}
+    b = _f32(bboxes, "bboxes")
+    r = torch.as_tensor(bbox_ref, dtype=torch.float32, device=b.device).reshape(4).contiguous()
+    out = torch.empty_like(b)
+    with torch.cuda.device(b.device):
+        _abi.check(_abi.lib.rod_bboxes_resize(r.data_ptr(), b.data_ptr(), out.data_ptr(), b.numel() // 4,
+                                              _abi.stream_ptr(b.device)))
+    return out
+
+
+def bboxes_jaccard(bbox_ref, bboxes, name=None):
+    """IoU of `bbox_ref` ((4,) or (N,4)) with bboxes (N,4) -> (N,), 0 where union <= 0."""
+    return _ref_op(_abi.lib.rod_bboxes_jaccard, bbox_ref, bboxes, 1)
+
+
+def bboxes_intersection(bbox_ref, bboxes, name=None):
+    """Intersection area over box area -> (N,), 0 where the box area <= 0."""
+    return _ref_op(_abi.lib.rod_bboxes_intersection, bbox_ref, bboxes, 1)
+
+
+def _nms(scores, bboxes, nms_threshold, keep_top_k):
+    s = _f32(scores, "scores")
+    b = _f32(bboxes, "bboxes")
+    if s.dim() != 2 or b.shape != s.shape + (4,):
+        raise ValueError("bboxes_nms_batch expects scores [B,N] and bboxes [B,N,4]")
+    B, N = s.shape
+    os_ = torch.empty((B, keep_top_k), dtype=torch.float32, device=s.device)
+    ob = torch.empty((B, keep_top_k, 4), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        _abi.check(_abi.lib.rod_bboxes_nms_batch(s.data_ptr(), b.data_ptr(), B, N, float(nms_threshold),
+                                                 int(keep_top_k), os_.data_ptr(), ob.data_ptr(), None,
+                                                 _abi.stream_ptr(s.device)))
+    return os_, ob
+
+
+def bboxes_nms(scores, bboxes, nms_threshold=0.5, keep_top_k=200, scope=None):
+    """Greedy NMS of one set: scores [N], bboxes [N,4] -> [keep_top_k], [keep_top_k,4],
+    in selection order, zero padded."""
+    s, b = _nms(scores.unsqueeze(0), bboxes.unsqueeze(0), nms_threshold, keep_top_k)
+    return s[0], b[0]
+
+
+def bboxes_nms_batch(scores, bboxes, nms_threshold=0.5, keep_top_k=200, scope=None):
+    """Batched / per-class-dict NMS: [B,N], [B,N,4] -> [B,keep_top_k], [B,keep_top_k,4]."""
+    if isinstance(scores, dict) or isinstance(bboxes, dict):
+        d_scores, d_bboxes = {}, {}
+        for c in scores.keys():
+            d_scores[c], d_bboxes[c] = bboxes_nms_batch(scores[c], bboxes[c], nms_threshold=nms_threshold,
+                                                        keep_top_k=keep_top_k)
+        return d_scores, d_bboxes
+    return _nms(scores, bboxes, nms_threshold, keep_top_k)

@@ -1,0 +1,176 @@
+"""CPU-side checks (no GPU compute): the C-ABI library loads and exports every symbol the
+header declares, the host mirror keeps the reference's names / signatures / error behaviour,
+and the NumPy anchor functions reproduce the reference fixtures."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import LAYOUTS, ROOT, golden, golden_anchors
+
+HEADER = os.path.join(ROOT, "include", "rodet_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rod_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import rodet_b200
+    from rodet_b200 import _abi
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(_abi.lib, n), "librodet_b200.so does not export %s" % n
+        assert n in _abi.SIGNATURES, "no ctypes signature for %s" % n
+    assert sorted(_abi.SIGNATURES) == names
+    assert _abi.lib.rod_version() == 1
+    assert isinstance(_abi.lib.rod_last_error(), bytes)
+
+
+def test_struct_layout_matches_header():
+    from rodet_b200 import _abi
+    assert ctypes.sizeof(_abi.Layout) == 4 * (2 + 9)
+    assert ctypes.sizeof(_abi.Layered) == 8 * 8 + 8 * 8
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    """No CPU fallback: importing the package without the .so raises ImportError."""
+    import importlib.util
+    import shutil
+    pkg_src = os.path.join(ROOT, "road-object-detection-for-bdd100k_b200")
+    dst = tmp_path / "pkgcopy"
+    shutil.copytree(pkg_src, dst, ignore=shutil.ignore_patterns("*.so", "csrc", "__pycache__"))
+    spec = importlib.util.spec_from_file_location("pkgcopy", dst / "__init__.py",
+                                                  submodule_search_locations=[str(dst)])
+    mod = importlib.util.module_from_spec(spec)
+    import sys
+    monkeypatch.setitem(sys.modules, "pkgcopy", mod)
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        spec.loader.exec_module(mod)
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    from rodet_b200 import config
+    from rodet_b200.utils import common_tools, net_tools
+    import rodet_b200.utils.tf_extended as tfe
+    with pytest.raises(ValueError, match="no CPU path"):
+        common_tools.centerBboxes_2_cornerBboxes(torch.zeros(3, 4))
+    with pytest.raises(ValueError, match="no CPU path"):
+        net_tools.refine_groundtruth(golden_anchors("tiny"), torch.zeros(2, 4), torch.zeros(2, dtype=torch.int64),
+                                     config.refine_method.JACCARD_BIGGER)
+    with pytest.raises(ValueError, match="no CPU path"):
+        tfe.bboxes_sort(torch.zeros(1, 8), torch.zeros(1, 8, 4), top_k=4)
+
+
+def test_reference_error_behaviour():
+    import torch
+    from rodet_b200 import config
+    from rodet_b200.utils import net_tools
+    a = golden_anchors("tiny")
+    with pytest.raises(ValueError, match="Not support now"):            # utils/net_tools.py:424
+        net_tools.refine_groundtruth(a, torch.zeros(2, 4), torch.zeros(2), config.refine_method.JACCARD_TOPK)
+    with pytest.raises(ValueError, match='Function parameter "method" wrong'):   # :426
+        net_tools.refine_groundtruth(a, torch.zeros(2, 4), torch.zeros(2), "bogus")
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """Entry points validate before touching the device: bad layouts / NULLs give ROD_E_INVALID."""
+    from rodet_b200 import _abi
+    lay = _abi.Layout()
+    lay.n_layers = 0
+    rc = _abi.lib.rod_arm_match_encode(lay, None, None, None, None, None, 1, None, 1, 1, 1, None, None, None, None, None, None)
+    assert rc == _abi.E_INVALID and b"n_layers" in _abi.lib.rod_last_error()
+    lay.n_layers, lay.n_total = 1, 8
+    lay.offset[0], lay.offset[1] = 0, 8
+    rc = _abi.lib.rod_arm_match_encode(lay, None, None, None, None, None, 1, None, 1, 1, 2, None, None, None, None, None, None)
+    assert rc == _abi.E_UNSUPPORTED and _abi.lib.rod_last_error() == b"Not support now"
+    rc = _abi.lib.rod_arm_match_encode(lay, None, None, None, None, None, 1, None, 1, 1, 1, None, None, None, None, None, None)
+    assert rc == _abi.E_INVALID
+    with pytest.raises(ValueError):
+        _abi.check(rc)
+    assert _abi.lib.rod_bboxes_sort(None, None, 1, 8, 4, None, None, None, None) == _abi.E_INVALID
+
+
+def test_signatures_match_reference():
+    """Same parameter names, order and defaults as the reference functions."""
+    from rodet_b200.utils import common_tools, net_tools
+    import rodet_b200.utils.tf_extended as tfe
+
+    def params(fn, n=None):
+        ps = list(inspect.signature(fn).parameters.values())
+        return [(p.name, p.default) for p in (ps[:n] if n else ps)]
+    E = inspect.Parameter.empty
+    assert params(net_tools.init_anchor) == [("n_layers", E)]
+    assert params(net_tools.anchors_one_layer) == [("img_shape", E), ("feat_shape", E), ("anchors_one_layer", E), ("dtype", np.float32)]
+    assert params(net_tools.anchors_all_layer) == [("img_shape", E), ("feats_shape", E), ("anchors_all_layer", E)]
+    assert params(net_tools.encode_locations_one_layer) == [("anchors_one_layer", E), ("center_bbox", E)]
+    assert params(net_tools.decode_locations_one_layer) == [("anchors_one_layer", E), ("offset_bboxes", E)]
+    assert params(net_tools.jaccard) == [("anchors", E), ("corner_bbox", E)]
+    assert params(net_tools.refine_groundtruth, 5) == [("anchors_all_layer", E), ("center_bboxes", E), ("labels", E), ("method", E), ("scope", "refine_encode")]
+    assert params(net_tools.det_groundtruth, 7) == [("refine_out", E), ("offset_gt", E), ("cbboxes", E), ("refine_labels", E), ("refine_pos_mask", E), ("anchors", E), ("scope", "det_encode")]
+    sel = [("select_threshold", None), ("num_classes", 21), ("ignore_class", 0), ("scope", None)]
+    assert params(net_tools.bboxes_select_one_layer) == [("predictions_layer", E), ("localizations_layer", E)] + sel
+    assert params(net_tools.bboxes_select_all_layers) == [("predictions_net", E), ("localizations_net", E)] + sel
+    assert params(net_tools.detected_bboxes, 7) == [("predictions", E), ("localisations", E), ("select_threshold", None), ("nms_threshold", 0.5), ("clipping_bbox", None), ("top_k", 800), ("keep_top_k", 200)]
+    assert params(tfe.bboxes_sort) == [("scores", E), ("bboxes", E), ("top_k", 400), ("scope", None)]
+    assert params(tfe.bboxes_sort_all_classes) == [("classes", E), ("scores", E), ("bboxes", E), ("top_k", 400), ("scope", None)]
+    assert params(tfe.bboxes_nms) == [("scores", E), ("bboxes", E), ("nms_threshold", 0.5), ("keep_top_k", 200), ("scope", None)]
+    assert params(tfe.bboxes_nms_batch) == [("scores", E), ("bboxes", E), ("nms_threshold", 0.5), ("keep_top_k", 200), ("scope", None)]
+    assert params(tfe.bboxes_clip) == [("bbox_ref", E), ("bboxes", E), ("scope", None)]
+    assert params(tfe.bboxes_resize) == [("bbox_ref", E), ("bboxes", E), ("name", None)]
+    assert params(tfe.bboxes_jaccard) == [("bbox_ref", E), ("bboxes", E), ("name", None)]
+    assert params(tfe.bboxes_intersection) == [("bbox_ref", E), ("bboxes", E), ("name", None)]
+    assert params(tfe.pad_axis) == [("x", E), ("offset", E), ("size", E), ("axis", 0), ("name", None)]
+    assert params(tfe.safe_divide) == [("numerator", E), ("denominator", E), ("name", None)]
+    assert params(common_tools.centerBboxes_2_cornerBboxes) == [("center_bboxes", E)]
+    assert params(common_tools.cornerBboxes_2_centerBboxes) == [("corner_bboxes", E)]
+
+
+@pytest.mark.parametrize("layout", ["418", "512", "tiny"])
+def test_host_anchor_functions_match_reference_fixture(layout):
+    from rodet_b200 import config
+    from rodet_b200.utils import net_tools
+    img, feats = LAYOUTS[layout]
+    config.img_size = img
+    sizes = net_tools.init_anchor(6)
+    assert np.array_equal(np.concatenate(list(sizes.values())), golden("anchors.npz")["%s_sizes_px" % layout])
+    ours = net_tools.anchors_all_layer(img, {"layer_%d" % (i + 1): f for i, f in enumerate(feats)}, sizes)
+    for o, r in zip(ours, golden_anchors(layout)):
+        for a, b in zip(o, r):
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+    assert net_tools.n_anchor_each_layer("mobilenet_v2") == [6, 9, 9, 9, 9, 9]
+    config.img_size = (418, 418)
+
+
+def test_config_values_match_reference():
+    from rodet_b200 import config
+    assert config.refine_pos_jac_val_all_layers == [0.2, 0.3, 0.4, 0.4, 0.3, 0.3]
+    assert config.det_pos_jac_val_all_layers == [0.5, 0.6, 0.7, 0.7, 0.6, 0.6]
+    assert config.total_obj_n == 11 and config.img_size == (418, 418)
+    assert config.normal_anchor_range == [0.05, 0.7] and config.special_anchor_range == [0.02, 0.03]
+    assert [m.value for m in config.refine_method] == [0, 1, 2]
+    assert config.feat_size_all_layers["mobilenet_v2"]["layer_1"] == (53, 53)
+
+
+def test_synth_is_deterministic_and_in_domain():
+    from rodet_b200 import synth
+    a, la, ca = synth.gt_batch(10, 4)
+    b, lb, cb = synth.gt_batch(10, 4)
+    assert np.array_equal(a, b) and np.array_equal(la, lb) and np.array_equal(ca, cb)
+    assert (ca >= 1).all() and (ca <= 100).all()
+    for i in range(4):
+        g = a[i, :ca[i]]
+        assert ((g[:, 2] - g[:, 0]) >= 1e-3).all() and ((g[:, 3] - g[:, 1]) >= 1e-3).all()
+        assert (g >= 0).all() and (g <= 1).all()
+        assert (la[i, :ca[i]] >= 1).all() and (la[i, :ca[i]] <= 10).all()
+    p = synth.class_probs(3, 500)
+    assert np.allclose(p.sum(1), 1, atol=1e-5) and p.dtype == np.float32
+    s = synth.stress_probs(3, 500)
+    assert (s >= np.float32(0.3)).all()

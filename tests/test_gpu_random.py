@@ -1,0 +1,204 @@
+"""GPU parity on the BASELINE-shaped synthetic workload against Tier B,
+at sizes the NumPy oracle finishes in seconds, plus size-independent properties at the full
+BASELINE batch sizes, plus the 1k-image bit-exactness run the north star asks for."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import LAYOUTS, golden_anchors
+from helpers import bit_equal, flat_from_list, to_cuda_list
+from oracle import restated as R
+
+pytestmark = pytest.mark.gpu
+N_PARITY_IMAGES = int(os.environ.get("RODET_PARITY_IMAGES", "1000"))
+
+
+@pytest.fixture(scope="module")
+def env(cuda_device):
+    import rodet_b200
+    from rodet_b200 import config, synth
+    from rodet_b200.utils import common_tools, net_tools
+
+    class NS:
+        pass
+    ns = NS()
+    ns.pkg, ns.config, ns.synth, ns.nt, ns.ct, ns.dev = rodet_b200, config, synth, net_tools, common_tools, cuda_device
+    ns.anchors = {k: golden_anchors(k) for k in ("418", "512")}
+    ns.otable = {k: R.AnchorTable(v) for k, v in ns.anchors.items()}
+    return ns
+
+
+def _gt_center(env, first, B):
+    corner, labels, counts = env.synth.gt_batch(first, B)
+    center = R.corner_to_center(corner)
+    for b in range(B):
+        center[b, counts[b]:] = 0
+    return corner, center.astype(np.float32), labels, counts
+
+
+def _arm_gpu(env, layout, center, labels, counts):
+    JB = env.config.refine_method.JACCARD_BIGGER
+    out = env.nt.refine_groundtruth(env.anchors[layout], torch.from_numpy(center).to(env.dev),
+                                    torch.from_numpy(labels).to(env.dev), JB,
+                                    gt_counts=torch.from_numpy(counts).to(env.dev), return_match_index=True)
+    return out
+
+
+def _check_arm(env, layout, first, B):
+    table = env.otable[layout]
+    corner, center, labels, counts = _gt_center(env, first, B)
+    # the host converts corner -> centre with the library too (train.py:109)
+    cen_gpu = env.ct.cornerBboxes_2_centerBboxes(torch.from_numpy(corner).to(env.dev)).cpu().numpy()
+    for b in range(B):
+        assert bit_equal(cen_gpu[b, :counts[b]], center[b, :counts[b]])
+    gt, cb, lab, pos, idx = _arm_gpu(env, layout, center, labels, counts)
+    g = [flat_from_list(x, t) for x, t in ((gt, 1), (cb, 1), (lab, 1), (pos, 1), (idx, 0))]
+    npos = 0
+    for b in range(B):
+        o = R.arm_match_encode(table, center[b, :counts[b]], labels[b, :counts[b]])
+        assert np.array_equal(g[3][b, :, 0], o[3]), "pos mask, image %d" % (first + b)
+        assert np.array_equal(g[4][b], o[4]), "match index, image %d" % (first + b)
+        assert np.array_equal(g[2][b, :, 0], o[2]), "labels, image %d" % (first + b)
+        assert bit_equal(g[1][b], o[1]) and bit_equal(g[0][b], o[0])
+        npos += int(o[3].sum())
+    return (gt, cb, lab, pos), g, npos
+
+
+@pytest.mark.parametrize("layout", ["512", "418"])
+def test_arm_odm_random_batch(env, layout):
+    B = 6
+    table = env.otable[layout]
+    (gt, cb, lab, pos), g, npos = _check_arm(env, layout, 100, B)
+    assert npos > 0
+    # ODM on the GPU's own ARM outputs (zero-copy per-layer views) + synthetic ARM head output
+    ro = np.stack([env.synth.head_offsets(100 + b, table.n) for b in range(B)])
+    # move half of the positives close to their target so both mask values occur
+    close = (np.arange(table.n)[None, :, None] % 2 == 0) & (g[3] > 0)
+    ro = np.where(close, g[0] + 0.05 * ro, ro).astype(np.float32)
+    ro_l = to_cuda_list(ro, table.shapes, (4,), env.dev)
+    det_gt, mask, dlab, iou = env.nt.det_groundtruth(ro_l, gt, cb, lab, pos, env.anchors[layout])
+    o = R.odm_target(table, ro, g[0], g[1], g[2][..., 0], g[3][..., 0])
+    assert np.array_equal(flat_from_list(mask, 1)[..., 0], o[1])
+    assert np.array_equal(flat_from_list(dlab, 1)[..., 0], o[2])
+    assert bit_equal(flat_from_list(iou, 0), o[3])
+    assert bit_equal(flat_from_list(det_gt, 1), o[0])
+    assert 0 < int(o[1].sum()) < int(g[3].sum())
+
+
+def _detect_inputs(env, layout, first, B, stress):
+    table = env.otable[layout]
+    mk = env.synth.stress_probs if stress else env.synth.class_probs
+    probs = np.stack([mk(first + b, table.n) for b in range(B)])
+    s = (0.05, 0.05) if stress else (0.1, 0.2)
+    ro = np.stack([env.synth.head_offsets(first + b, table.n, 0, *s) for b in range(B)])
+    do = np.stack([env.synth.head_offsets(first + b, table.n, 1, *s) for b in range(B)])
+    return probs, ro, do
+
+
+def _check_detect(env, layout, first, B, stress, sthr=0.3, nthr=0.45, topk=400, keep=200):
+    table = env.otable[layout]
+    probs, ro, do = _detect_inputs(env, layout, first, B, stress)
+    preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+    rs, rb, counts = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=sthr,
+                                                   nms_threshold=nthr, top_k=topk, keep_top_k=keep, return_counts=True)
+    boxes = R.decode_corner(table, ro, do)
+    o_s, o_b = R.detected_bboxes(probs, boxes, sthr, nthr, None, topk, keep)
+    ndet = 0
+    for c in range(1, 11):
+        assert bit_equal(rs[c].cpu().numpy(), o_s[c]), "scores class %d images %d.." % (c, first)
+        assert bit_equal(rb[c].cpu().numpy(), o_b[c]), "boxes class %d images %d.." % (c, first)
+        ndet += int((o_s[c] != 0).sum())
+    # drop-in sequence: decode per layer -> c2c -> detected_bboxes must give the same
+    locs = [env.ct.centerBboxes_2_cornerBboxes(env.nt.decode_locations_one_layer(a, r + d))
+            for a, r, d in zip(env.anchors[layout], ro_l, do_l)]
+    assert bit_equal(flat_from_list(locs, 1), boxes)
+    rs2, rb2 = env.nt.detected_bboxes(preds, locs, select_threshold=sthr, nms_threshold=nthr, top_k=topk, keep_top_k=keep)
+    for c in range(1, 11):
+        assert torch.equal(rs2[c], rs[c]) and bit_equal(rb2[c].cpu().numpy(), rb[c].cpu().numpy())
+    return ndet
+
+
+@pytest.mark.parametrize("layout,stress", [("512", False), ("512", True), ("418", False)])
+def test_detect_random_batch(env, layout, stress):
+    assert _check_detect(env, layout, 200, 3, stress) > 0
+
+
+def test_detect_script_defaults(env):
+    """evaluate.py:58-65 (0.3 / 0.4 / 400 / 200), predict.py:136-137 (0.1 / 0.4) and the
+    signature defaults of detected_bboxes (None / 0.5 / 800 / 200)."""
+    _check_detect(env, "418", 300, 1, False, 0.3, 0.4, 400, 200)
+    _check_detect(env, "418", 301, 1, False, 0.1, 0.4, 400, 200)
+    _check_detect(env, "418", 302, 1, False, None, 0.5, 800, 200)
+
+
+def test_thousand_images_bit_exact(env):
+    """North star: match indices, positive masks and NMS keep sets bit-exact on 1k synthetic
+    images (512x512 layout).  RODET_PARITY_IMAGES shortens the run."""
+    n = N_PARITY_IMAGES
+    step = 8
+    npos = ndet = 0
+    for first in range(0, n, step):
+        B = min(step, n - first)
+        _, _, p = _check_arm(env, "512", 10_000 + first, B)
+        npos += p
+    for first in range(0, n, 4):
+        ndet += _check_detect(env, "512", 20_000 + first, min(4, n - first), stress=(first % 40 == 0))
+    assert npos > n and ndet > n
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def test_fullsize_properties_match_encode(env):
+    """BASELINE config 2 (batch 32): properties that need no oracle."""
+    B, layout = 32, "512"
+    table = env.otable[layout]
+    corner, center, labels, counts = _gt_center(env, 5000, B)
+    gt, cb, lab, pos, idx = _arm_gpu(env, layout, center, labels, counts)
+    P = flat_from_list(pos, 1)[..., 0]
+    I = flat_from_list(idx, 0)
+    L = flat_from_list(lab, 1)[..., 0]
+    C = flat_from_list(cb, 1)
+    G = flat_from_list(gt, 1)
+    assert set(np.unique(P)) <= {0, 1}
+    assert (I >= 0).all() and (I < counts[:, None]).all()
+    for b in range(B):
+        m = P[b] > 0
+        assert bit_equal(C[b][m], center[b][I[b][m]])             # matched box is the argmax box
+        assert np.array_equal(L[b][m], labels[b][I[b][m]].astype(np.int32))
+        assert not C[b][~m].any() and not G[b][~m].any() and not L[b][~m].any()
+    # decode(encode(gt)) round trip recovers the matched boxes on positives
+    dec = [env.nt.decode_locations_one_layer(a, g) for a, g in zip(env.anchors[layout], gt)]
+    D = flat_from_list(dec, 1)
+    m = P > 0
+    np.testing.assert_allclose(D[m], C[m], rtol=2e-5, atol=2e-6)
+    # idempotence: a second launch gives identical bits
+    gt2 = _arm_gpu(env, layout, center, labels, counts)[0]
+    assert all(torch.equal(a, b) for a, b in zip(gt, gt2))
+
+
+def test_fullsize_properties_detect(env):
+    """BASELINE configs 3 and 5 (batch 64, normal and stress scores)."""
+    layout, B, keep, nthr = "512", 64, 200, 0.45
+    table = env.otable[layout]
+    for stress in (False, True):
+        probs, ro, do = _detect_inputs(env, layout, 7000, B, stress)
+        preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
+        ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+        rs, rb, counts = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=0.3,
+                                                       nms_threshold=nthr, top_k=400, keep_top_k=keep, return_counts=True)
+        for c in (1, 5, 10):
+            s, b = rs[c].cpu().numpy(), rb[c].cpu().numpy()
+            assert (np.diff(s, axis=1) <= 0).all()                      # descending, zero padded at the end
+            cnt = counts[c].cpu().numpy()
+            assert np.array_equal(cnt, (s != 0).sum(1))
+            assert ((s >= np.float32(0.3)) | (s == 0)).all()
+            for img in (0, B - 1):
+                k = cnt[img]
+                assert not b[img, k:].any()
+                iou = R.nms_iou_matrix(b[img, :k])
+                np.fill_diagonal(iou, 0)
+                assert (iou <= np.float32(nthr)).all()                  # survivors do not suppress each other
+        if stress:
+            assert int(counts[1:].sum()) >= int(0.9 * 10 * B * keep)
