@@ -43,6 +43,8 @@ struct GatherBoxes {       // fused: candidates come sorted from the top-k kerne
   const float* center;     // anchors (acy,acx,ah,aw)
   Layout L;
   int has_loc, batch;
+  const unsigned* over_cnt;   // when set: only segments whose streaming list overflowed run here
+  unsigned over_cap;
 };
 
 template <bool FUSED>
@@ -66,6 +68,7 @@ nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ Gath
   const long long r = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (FUSED && (int)(r / gsrc.batch) == ignore_class) return;
+  if (FUSED && gsrc.over_cnt != nullptr && gsrc.over_cnt[r] <= gsrc.over_cap) return;
   if (tid == 0) { s_last = 0; s_nsel = 0; }
   __syncthreads();
 
@@ -211,6 +214,12 @@ static size_t nms_smem_bytes(int n, int keep, bool dense) {
 
 int launch_topk_selected(const SelectedScores& src, long long rows, int k, float* out_scores, int32_t* out_idx,
                          cudaStream_t st);
+size_t stream_workspace_bytes(int batch, int n_classes, int top_k);
+int launch_detect_stream(const Layout& L, const float* anchors_center, const LayeredF& probs, const LayeredF* loc,
+                         const LayeredF* refine, const LayeredF* det, int batch, int C, int ignore_class,
+                         float select_thr, float nms_thr, int top_k, int keep, const float* clip, float* out_scores,
+                         float* out_boxes, int32_t* out_counts, void* ws, const unsigned** cnt_out, int* cap_out,
+                         cudaStream_t st);
 
 }  // namespace rod
 
@@ -243,7 +252,7 @@ extern "C" size_t rod_detect_workspace_bytes(const rod_layout_t* layout, int bat
   (void)layout;
   if (batch <= 0 || n_classes <= 0 || top_k <= 0) return 256;
   const size_t per = (size_t)batch * n_classes * top_k;
-  return ((per * 4 + 255) / 256) * 256 * 2 + 256;
+  return ((per * 4 + 255) / 256) * 256 * 2 + 256 + rod::stream_workspace_bytes(batch, n_classes, top_k);
 }
 
 extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_center,
@@ -283,16 +292,36 @@ extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_cente
   float* ws_scores = reinterpret_cast<float*>(workspace);
   int32_t* ws_idx = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + per);
 
+  // ---- fast path (select_threshold > 0): streaming histogram select + per-segment sort/decode/NMS
+  const LayeredF probs_l = to_layered_f(predictions, nl);
+  const unsigned* over_cnt = nullptr;
+  int over_cap = 0;
+  if (select_threshold > 0.f) {
+    const LayeredF loc_l = localizations ? to_layered_f(localizations, nl) : probs_l;
+    const LayeredF ref_l = localizations ? probs_l : to_layered_f(refine_out, nl);
+    const LayeredF det_l = localizations ? probs_l : to_layered_f(det_out, nl);
+    void* ws_stream = reinterpret_cast<unsigned char*>(workspace) + 2 * per;
+    if ((rc = launch_detect_stream(L, anchors_center, probs_l, localizations ? &loc_l : nullptr,
+                                   localizations ? nullptr : &ref_l, localizations ? nullptr : &det_l, batch,
+                                   n_classes, ignore_class, select_threshold, nms_threshold, top_k, keep_top_k,
+                                   clip_box, out_scores, out_bboxes, out_counts, ws_stream, &over_cnt, &over_cap, st)))
+      return rc;
+  } else if (out_counts) {
+    ROD_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * rows, st));
+  }
+
+  // ---- general exact path: every segment when thr <= 0, else only segments whose list overflowed
   SelectedScores src;
-  src.probs = to_layered_f(predictions, nl);
+  src.probs = probs_l;
   src.L = L;
   src.n_classes = n_classes;
   src.ignore_class = ignore_class;
   src.batch = batch;
   src.thr = select_threshold;
+  src.over_cnt = over_cnt;
+  src.over_cap = (unsigned)over_cap;
   if ((rc = launch_topk_selected(src, rows, top_k, ws_scores, ws_idx, st))) return rc;
 
-  if (out_counts) ROD_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * rows, st));
   GatherBoxes g;
   g.scores = ws_scores;
   g.idx = ws_idx;
@@ -303,6 +332,8 @@ extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_cente
   g.center = anchors_center;
   g.L = L;
   g.batch = batch;
+  g.over_cnt = over_cnt;
+  g.over_cap = (unsigned)over_cap;
   const size_t smem = nms_smem_bytes(top_k, keep_top_k, false);
   ROD_REQUIRE(smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep_top_k, smem);
   auto k = nms_kernel<true>;

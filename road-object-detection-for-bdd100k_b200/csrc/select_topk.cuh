@@ -24,8 +24,12 @@ struct SelectedScores {
   Layout L;
   int n_classes, ignore_class, batch;
   float thr;
+  const unsigned* over_cnt;   // when set: only segments whose streaming list overflowed are active
+  unsigned over_cap;
   __device__ __forceinline__ int size() const { return L.n_total; }
-  __device__ __forceinline__ bool row_active(long long r) const { return (int)(r / batch) != ignore_class; }
+  __device__ __forceinline__ bool row_active(long long r) const {
+    return (int)(r / batch) != ignore_class && (over_cnt == nullptr || over_cnt[r] > over_cap);
+  }
   __device__ __forceinline__ float fetch(long long r, int i, bool& real) const {
     const int c = (int)(r / batch), b = (int)(r % batch);
     const int l = layer_of(L, i);

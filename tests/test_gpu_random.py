@@ -202,3 +202,40 @@ def test_fullsize_properties_detect(env):
                 assert (iou <= np.float32(nthr)).all()                  # survivors do not suppress each other
         if stress:
             assert int(counts[1:].sum()) >= int(0.9 * 10 * B * keep)
+
+
+def test_detect_heavy_ties_overflow_fallback(env):
+    """Scores quantised to 1/8: thousands of exactly equal scores per class, so the streaming
+    candidate list overflows and the exact general kernels must take over (lowest-index ties)."""
+    layout, B = "512", 2
+    table = env.otable[layout]
+    probs, ro, do = _detect_inputs(env, layout, 400, B, stress=True)
+    probs = (np.round(probs * 8) / 8).astype(np.float32)
+    probs[1, :, 3] = np.float32(0.5)                      # one class entirely tied
+    preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+    rs, rb, counts = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=0.3,
+                                                   nms_threshold=0.45, top_k=400, keep_top_k=200, return_counts=True)
+    o_s, o_b = R.detected_bboxes(probs, R.decode_corner(table, ro, do), 0.3, 0.45, None, 400, 200)
+    for c in range(1, 11):
+        assert bit_equal(rs[c].cpu().numpy(), o_s[c]), c
+        assert bit_equal(rb[c].cpu().numpy(), o_b[c]), c
+        assert np.array_equal(counts[c].cpu().numpy(), (o_s[c] != 0).sum(1))
+
+
+def test_detect_fewer_candidates_than_topk(env):
+    """High threshold: fewer than top_k candidates per class, some classes empty."""
+    layout, B = "512", 2
+    table = env.otable[layout]
+    probs, ro, do = _detect_inputs(env, layout, 410, B, stress=False)
+    probs[0, :, 4] = np.float32(0.01)                     # class 4 of image 0: no candidate at all
+    preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+    rs, rb = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=0.9,
+                                           nms_threshold=0.45, top_k=400, keep_top_k=200)
+    o_s, o_b = R.detected_bboxes(probs, R.decode_corner(table, ro, do), 0.9, 0.45, None, 400, 200)
+    n = 0
+    for c in range(1, 11):
+        assert bit_equal(rs[c].cpu().numpy(), o_s[c]) and bit_equal(rb[c].cpu().numpy(), o_b[c]), c
+        n += int((o_s[c] != 0).sum())
+    assert n > 0 and not rs[4][0].any()
