@@ -21,7 +21,8 @@ namespace rod {
 
 constexpr int kBins = 1024;
 constexpr int kStreamBlock = 256;
-constexpr int kSegBlock = 256;
+constexpr int kSegBlock = 128;
+constexpr int kSegWarps = kSegBlock / 32;
 
 __device__ __forceinline__ int score_bin(float s) {
   // monotone non-decreasing in s for s > 0; only resolution (never correctness) depends on it
@@ -54,15 +55,24 @@ __device__ __forceinline__ void for_each_score(const Layout& L, const LayeredF& 
     int f = lo + head + 4 * threadIdx.x;
     int n = f / C, c = f - n * C;
     const int step = 4 * blockDim.x, step_n = step / C, step_c = step - step_n * C;
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-      const float4 x = ldg4(slab + f);
-      int nn = n, cc = c;
-      fn(x.x, nn, cc); if (++cc == C) { cc = 0; ++nn; }
-      fn(x.y, nn, cc); if (++cc == C) { cc = 0; ++nn; }
-      fn(x.z, nn, cc); if (++cc == C) { cc = 0; ++nn; }
-      fn(x.w, nn, cc);
-      f += step; n += step_n; c += step_c;
-      if (c >= C) { c -= C; ++n; }
+    for (int v = threadIdx.x; v < nvec; v += 4 * blockDim.x) {
+      // 4 independent 16 B loads in flight per thread before any is consumed
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v + u * (int)blockDim.x < nvec) x[u] = ldg4(slab + f + u * step);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (v + u * (int)blockDim.x < nvec) {
+          int nn = n, cc = c;
+          fn(x[u].x, nn, cc); if (++cc == C) { cc = 0; ++nn; }
+          fn(x[u].y, nn, cc); if (++cc == C) { cc = 0; ++nn; }
+          fn(x[u].z, nn, cc); if (++cc == C) { cc = 0; ++nn; }
+          fn(x[u].w, nn, cc);
+        }
+        f += step; n += step_n; c += step_c;
+        if (c >= C) { c -= C; ++n; }
+      }
     }
   }
 }
@@ -169,6 +179,19 @@ struct SegParams {
   const float* clip;
 };
 
+// bytes of the aliased region: sort keys, later {kept boxes, overlap words, batch rows, kept areas}
+__host__ __device__ inline size_t seg_region_a(int cap, int keep) {
+  const size_t a = (size_t)cap * 8, b = (size_t)keep * (16 + 8 + 4) + 128 * 8;
+  return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+
+// one bitonic compare-exchange between lanes `lane` and `lane ^ stride` (element index e)
+__device__ __forceinline__ unsigned long long bitonic_cx(unsigned long long v, int e, int lane, int size, int stride) {
+  const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, stride);
+  const bool take_max = (((e & size) == 0) == ((lane & stride) == 0));
+  return take_max ? (v > o ? v : o) : (v < o ? v : o);
+}
+
 // exact "fdiv_rn(inter, den) > thr" with a division-free fast path (thr >= 0, den > 0)
 __device__ __forceinline__ bool iou_exceeds(float inter, float den, float thr) {
   const float p = __fmul_rn(thr, den);
@@ -182,18 +205,23 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned* __restrict__
                const unsigned long long* __restrict__ g_list, float* __restrict__ out_scores,
                float* __restrict__ out_boxes, int32_t* __restrict__ out_counts) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  // [0, A): sort keys (cap x 8 B), later aliased by the suppression mask (m x W x 8 B)
-  // then boxes (k x 16), normalised boxes (k x 16), area, score (k x 4 each), selected (keep x 4)
+  // region A: sort keys (cap x 8 B); after the gather it is re-used for the NMS working set
+  //           (kept boxes, kept areas, overlap words, intra-batch rows)
+  // then: boxes (k x 16), normalised boxes (k x 16), area, score (k x 4 each), kept positions (keep x 4)
   const int cap = P.cap, k = P.k, keep = P.keep;
-  const int Wmax = (k + 63) >> 6;
-  const size_t regionA = (max((size_t)cap * 8, (size_t)k * Wmax * 8) + 15) & ~(size_t)15;
+  const size_t regionA = seg_region_a(cap, keep);
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_raw);
-  unsigned long long* s_mask = s_keys;
+  float4* s_kbox = reinterpret_cast<float4*>(s_raw);                                   // [keep]
+  unsigned long long* s_ov = reinterpret_cast<unsigned long long*>(s_kbox + keep);     // [keep]
+  unsigned long long* s_bm = s_ov + keep;                                              // [64] batch rows: overlap words
+  unsigned long long* s_cm = s_bm + 64;                                                // [64] batch columns: suppressors
+  float* s_karea = reinterpret_cast<float*>(s_cm + 64);                                // [keep]
   float4* s_box = reinterpret_cast<float4*>(s_raw + regionA);
   float4* s_nbox = s_box + k;
   float* s_area = reinterpret_cast<float*>(s_nbox + k);
   float* s_score = s_area + k;
   int* s_selected = reinterpret_cast<int*>(s_score + k);
+  __shared__ unsigned long long s_dead, s_sel;
   __shared__ int s_nsel;
 
   const long long r = blockIdx.x;
@@ -204,13 +232,25 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned* __restrict__
   const int cnt = (int)cnt_raw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- 1. sort the candidate list: descending (score bits, ~anchor)
-  int n2 = 1;
+  // ---- 1. sort the candidate list: descending (score bits, ~anchor).  Bitonic network; every
+  // compare-exchange with stride < 32 runs in registers with warp shuffles (one element per lane),
+  // only strides >= 32 go through shared memory.
+  int n2 = 32;
   while (n2 < cnt) n2 <<= 1;
   for (int j = tid; j < n2; j += kSegBlock) s_keys[j] = j < cnt ? g_list[r * cap + j] : 0ull;
   __syncthreads();
-  for (int size = 2; size <= n2; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+  for (int g = warp; g < (n2 >> 5); g += kSegWarps) {            // sizes 2..32 entirely in registers
+    const int e = (g << 5) + lane;
+    unsigned long long v = s_keys[e];
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) v = bitonic_cx(v, e, lane, size, stride);
+    s_keys[e] = v;
+  }
+  __syncthreads();
+  for (int size = 64; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride >= 32; stride >>= 1) {
       for (int t = tid; t < (n2 >> 1); t += kSegBlock) {
         const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
         const bool desc = ((lo & size) == 0);
@@ -219,6 +259,15 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned* __restrict__
       }
       __syncthreads();
     }
+    for (int g = warp; g < (n2 >> 5); g += kSegWarps) {
+      const int e = (g << 5) + lane;
+      unsigned long long v = s_keys[e];
+#pragma unroll
+      for (int stride = 16; stride > 0; stride >>= 1) v = bitonic_cx(v, e, lane, size, stride);
+      s_keys[e] = v;
+    }
+    __syncthreads();
+  }
   const int m = min(cnt, k);                          // real candidates entering NMS
 
   // ---- 2. gather / decode the m boxes (evaluate.py:141-142), select-stage mask is 1 for all of them
@@ -246,61 +295,114 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned* __restrict__
   }
   __syncthreads();                                    // keys are dead from here: region A becomes the mask
 
-  // ---- 3. suppression bitmask, upper triangle; item = (row i, 64-bit word w)
-  const int W = (m + 63) >> 6;
+  // ---- 3. greedy NMS in batches of 64 candidates against the kept list.
+  // A candidate is kept iff no earlier KEPT box has IoU > thr with it (tf.image.non_max_suppression).
+  // Per batch: (a) ballot the exact "positive intersection" predicate of the 64 candidates (two
+  // per lane, in registers) against every kept box (broadcast from shared memory) and against the
+  // batch itself; (b) run the IoU test only on intersecting pairs; (c) one warp resolves the
+  // 64 x 64 intra-batch dependencies serially; (d) survivors join the kept list.
   const float thr = P.nms_thr;
-  for (int t = tid; t < m * W; t += kSegBlock) {
-    const int i = t / W, w = t - i * W;
-    unsigned long long bits = 0ull;
-    if (w >= (i >> 6)) {
-      const float4 bi = s_nbox[i];
-      const float ai = s_area[i];
-      const int j0 = w << 6;
-      const int jbeg = max(j0, i + 1), jend = min(j0 + 64, m);
-      // phase 1: exact "positive intersection" predicate, branch-free
-      unsigned long long maybe = 0ull;
-      for (int j = jbeg; j < jend; ++j) {
-        const float4 bj = s_nbox[j];
-        const bool ov = (fminf(bi.z, bj.z) > fmaxf(bi.x, bj.x)) && (fminf(bi.w, bj.w) > fmaxf(bi.y, bj.y));
-        maybe |= (unsigned long long)ov << (j - j0);
-      }
-      // phase 2: IoU test only for intersecting pairs
-      while (maybe) {
-        const int q = __ffsll((long long)maybe) - 1;
-        maybe &= maybe - 1;
-        const int j = j0 + q;
-        const float4 bj = s_nbox[j];
-        const float ih = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
-        const float iw = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
-        const float inter = __fmul_rn(ih, iw);
-        const float den = __fsub_rn(__fadd_rn(ai, s_area[j]), inter);
-        const bool sup = (thr >= 0.f && den > 1e-30f) ? iou_exceeds(inter, den, thr) : (__fdiv_rn(inter, den) > thr);
-        bits |= (unsigned long long)sup << q;
+  const float4 none = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+  int nk = 0;
+  for (int p0 = 0; p0 < m && nk < keep; p0 += 64) {
+    const int nb = min(64, m - p0);
+    const int c0 = p0 + lane, c1 = c0 + 32;
+    const float4 b0 = c0 < m ? s_nbox[c0] : none;
+    const float4 b1 = c1 < m ? s_nbox[c1] : none;
+    // (a) overlap words: kept rows j = warp, warp+8, ... ; batch rows r = warp*8 .. warp*8+7
+#pragma unroll 4
+    for (int j = warp; j < nk; j += kSegWarps) {
+      const float4 kb = s_kbox[j];
+      const bool q0 = (kb.z > b0.x) && (b0.z > kb.x) && (kb.w > b0.y) && (b0.w > kb.y);
+      const bool q1 = (kb.z > b1.x) && (b1.z > kb.x) && (kb.w > b1.y) && (b1.w > kb.y);
+      const unsigned lo = __ballot_sync(0xffffffffu, q0), hi = __ballot_sync(0xffffffffu, q1);
+      if (lane == 0) s_ov[j] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 64 / kSegWarps; ++rr) {
+      const int rrow = warp * (64 / kSegWarps) + rr;
+      if (rrow < nb) {
+        const float4 bi = s_nbox[p0 + rrow];
+        const bool q0 = (bi.z > b0.x) && (b0.z > bi.x) && (bi.w > b0.y) && (b0.w > bi.y);
+        const bool q1 = (bi.z > b1.x) && (b1.z > bi.x) && (bi.w > b1.y) && (b1.w > bi.y);
+        const unsigned lo = __ballot_sync(0xffffffffu, q0), hi = __ballot_sync(0xffffffffu, q1);
+        unsigned long long word = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        word &= (rrow == 63) ? 0ull : ~((2ull << rrow) - 1ull);       // columns after the row only
+        if (lane == 0) s_bm[rrow] = word;
       }
     }
-    s_mask[(size_t)i * W + w] = bits;
-  }
-  __syncthreads();
-
-  // ---- 4. greedy sweep (warp 0): dead candidates cost nothing, a survivor costs two LDS
-  if (warp == 0) {
-    unsigned long long dead = 0ull;                   // lane w owns word w (W <= 16)
-    int nsel = 0;
-    for (int w = 0; w < W && nsel < keep; ++w) {
-      unsigned long long alive = ~__shfl_sync(0xffffffffu, dead, w);
-      if (w == W - 1 && (m & 63)) alive &= (1ull << (m & 63)) - 1ull;
-      while (alive && nsel < keep) {
-        const int q = __ffsll((long long)alive) - 1;
-        const int p = (w << 6) + q;
-        if (lane == 0) s_selected[nsel] = p;
-        ++nsel;
-        const unsigned long long diag = s_mask[(size_t)p * W + w];
-        if (lane < W) dead |= s_mask[(size_t)p * W + lane];
-        alive &= ~(diag | (1ull << q));
+    if (tid == 0) s_dead = 0ull;
+    if (tid < 64) s_cm[tid] = 0ull;
+    __syncthreads();
+    // (b) exact IoU > thr on the intersecting pairs
+    for (int t = tid; t < nk + nb; t += kSegBlock) {
+      const bool vs_kept = t < nk;
+      unsigned long long maybe = vs_kept ? s_ov[t] : s_bm[t - nk];
+      if (maybe) {
+        const float4 bi = vs_kept ? s_kbox[t] : s_nbox[p0 + t - nk];
+        const float ai = vs_kept ? s_karea[t] : s_area[p0 + t - nk];
+        unsigned long long bits = 0ull;
+        while (maybe) {
+          const int q = __ffsll((long long)maybe) - 1;
+          maybe &= maybe - 1;
+          const float4 bj = s_nbox[p0 + q];
+          const float ih = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+          const float iw = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+          const float inter = __fmul_rn(ih, iw);
+          const float den = __fsub_rn(__fadd_rn(ai, s_area[p0 + q]), inter);
+          const bool sup = (thr >= 0.f && den > 1e-30f) ? iou_exceeds(inter, den, thr) : (__fdiv_rn(inter, den) > thr);
+          bits |= (unsigned long long)sup << q;
+        }
+        if (vs_kept) {
+          if (bits) atomicOr(&s_dead, bits);
+        } else {
+          // column view of the intra-batch suppression relation: s_cm[q] = rows that suppress q
+          const unsigned long long me = 1ull << (t - nk);
+          while (bits) {
+            const int q = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            atomicOr(&s_cm[q], me);
+          }
+        }
       }
     }
-    if (lane == 0) s_nsel = nsel;
+    __syncthreads();
+    // (c) resolve the intra-batch dependencies (warp 0): candidate q is dead if a KEPT earlier
+    // candidate suppresses it, kept once no undecided earlier candidate could.  Each round decides
+    // at least the lowest undecided candidate; chains are short, so a few rounds suffice.
+    if (warp == 0) {
+      unsigned long long U = ~s_dead;
+      if (nb < 64) U &= (1ull << nb) - 1ull;
+      unsigned long long K = 0ull;
+      const unsigned long long cm0 = s_cm[lane], cm1 = s_cm[lane + 32];
+      while (U) {
+        const bool u0 = (U >> lane) & 1ull, u1 = (U >> (lane + 32)) & 1ull;
+        const bool d0 = u0 && (cm0 & K), d1 = u1 && (cm1 & K);
+        const bool k0 = u0 && !d0 && !(cm0 & U), k1 = u1 && !d1 && !(cm1 & U);
+        const unsigned long long newK = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+        const unsigned long long newD = (unsigned long long)__ballot_sync(0xffffffffu, d0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, d1) << 32);
+        K |= newK;
+        U &= ~(newK | newD);
+      }
+      const int room = keep - nk;                     // greedy stops once keep boxes are selected
+      while (__popcll(K) > room) K &= ~(1ull << (63 - __clzll((long long)K)));
+      if (lane == 0) s_sel = K;
+    }
+    __syncthreads();
+    // (d) append the survivors to the kept list, in order
+    const unsigned long long sel = s_sel;
+    if (tid < 64 && ((sel >> tid) & 1ull)) {
+      const int pos = nk + __popcll(sel & ((1ull << tid) - 1ull));
+      s_selected[pos] = p0 + tid;
+      s_kbox[pos] = s_nbox[p0 + tid];
+      s_karea[pos] = s_area[p0 + tid];
+    }
+    nk += __popcll(sel);
+    __syncthreads();
   }
+  if (tid == 0) s_nsel = nk;
   __syncthreads();
 
   // ---- 5. emit keep rows: survivors in order, then pad_axis zeros (clip applies to all rows)
@@ -331,11 +433,8 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned* __restrict__
 }
 
 static size_t seg_smem_bytes(int cap, int k, int keep) {
-  const int W = (k + 63) >> 6;
-  const size_t a = (size_t)cap * 8, bmask = (size_t)k * W * 8;
-  return (((a > bmask ? a : bmask) + 15) & ~(size_t)15) + (size_t)k * (16 + 16 + 4 + 4) + (size_t)keep * 4 + 16;
+  return seg_region_a(cap, keep) + (size_t)k * (16 + 16 + 4 + 4) + (size_t)keep * 4 + 16;
 }
-
 static int stream_cap(int k) {
   int p = 1;
   while (p < k) p <<= 1;
