@@ -5,16 +5,22 @@
 // With thr > 0 every entry the select stage zeroes (score*0, box*0) ranks below every real
 // candidate and is indistinguishable from pad_axis's zero padding in the output, so only the
 // candidates with p >= thr matter.  Per (class, image) segment:
-//   A1  hist_kernel     one coalesced pass over the [B,N,C] scores; candidates are counted in a
-//                       per-segment 1024-bin histogram (shared-memory atomics, flushed once).
+//   A1  scan_kernel<0>  ONE pass over the [B,N,C] scores.  256-anchor tiles are staged into shared
+//                       memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered); one
+//                       thread per anchor.  Candidates (p >= thr) are counted in a per-segment
+//                       1024-bin histogram (packed 16-bit shared-memory counters, flushed once per
+//                       CTA) and, while they are sparse, appended to the segment's candidate list
+//                       (warp-aggregated, staged per tile).  A segment whose candidates are not sparse
+//                       (> 64 per class per tile, or > 4096 in total) is flagged "dense".
 //   T   thresh_kernel   suffix scan of the histogram -> the lowest bin still inside the top_k.
-//   A2  collect_kernel  second pass (largely L2 hits): candidates at or above that bin are
-//                       appended to the segment's list as (score bits, ~anchor) 64-bit keys.
-//   B   segment_kernel  one CTA per segment: bitonic sort of the list (score desc, anchor asc =
-//                       tf.nn.top_k order), keep the first top_k, gather + decode their boxes,
-//                       bitmask NMS, write keep_top_k rows zero padded.
-// A list that overflows (massive score ties at the threshold bin) is left to the exact
-// general kernels (topk_segment_kernel + nms_kernel), which re-run only for flagged segments.
+//   A2  scan_kernel<1>  only for dense segments: second pass that appends the candidates at or
+//                       above the threshold bin (the NMS-stress workload takes this route).
+//   B   segment_kernel  one CTA per segment: filter the list by the threshold bin, bitonic sort
+//                       (score desc, anchor asc = tf.nn.top_k order), keep the first top_k, gather +
+//                       decode their boxes, batched greedy NMS, write keep_top_k rows zero padded.
+// A list that overflows the sort capacity (massive score ties at the threshold bin) is left to the
+// exact general kernels (topk_segment_kernel + nms_kernel), which re-run only for flagged segments.
+// Prediction depths other than 11 use the plain-load two-pass kernels (hist_kernel, collect_kernel).
 #include "select_topk.cuh"
 
 namespace rod {
@@ -106,6 +112,191 @@ hist_kernel(const __grid_constant__ StreamParams P, unsigned* __restrict__ g_his
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-staged scan (prediction depth C known at compile time)
+// ------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 256;     // threads = anchors per tile
+constexpr int kListCap = 4096;      // per segment candidate list entries (8 B each)
+constexpr int kMaxChunks = 64;      // CTAs per image; each owns kListCap / chunks list slots per class
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// 1-D bulk copy global -> shared, completion signalled on `bar` (bytes % 16 == 0, 16 B aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+struct ScanParams {
+  LayeredF probs;
+  Layout L;
+  int ignore_class, batch, chunk;      // chunk = anchors per CTA (multiple of 256)
+  int chunks, spc;                     // CTAs per image, list slots per (class, CTA)
+  float thr;
+  unsigned* g_hist;                    // [rows][kBins]
+  unsigned* g_cnt1;                    // [rows][kMaxChunks] candidates written by each sparse-pass CTA
+  unsigned* g_cnt2;                    // [rows] candidates appended by the dense pass
+  unsigned* g_flag;                    // [rows] != 0: some CTA ran out of list slots => dense segment
+  const int* g_tbin;                   // [rows] (MODE 1)
+  unsigned long long* g_list;          // [rows][kListCap]
+};
+
+template <int MODE, int C>
+struct ScanShared {
+  unsigned hist[MODE == 0 ? C * kBins / 2 : 1];                 // two 16-bit counters per word
+  unsigned cnt[C];
+  int tb[C];
+};
+
+// One anchor per lane; `row` points at its C scores (shared-memory tile, or global for the few
+// unaligned head / tail anchors).  MODE 0: histogram + append to this CTA's private slice of the
+// segment's list while it has room.  MODE 1: append candidates at or above the threshold bin.
+template <int MODE, int C>
+__device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE, C>& S, bool valid,
+                                            const float* __restrict__ row, int n, int b) {
+  unsigned cand = 0;
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float s = row[c];
+      bool p = s >= P.thr;
+      if constexpr (MODE == 1) p = p && score_bin(s) >= S.tb[c];
+      cand |= (unsigned)p << c;
+    }
+    cand &= ~(1u << P.ignore_class);
+  }
+  const unsigned nkey = (unsigned)(~(unsigned)n);
+  while (cand) {
+    const int c = __ffs(cand) - 1;
+    cand &= cand - 1;
+    const float s = row[c];
+    const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | nkey;
+    const size_t r = (size_t)c * P.batch + b;
+    if constexpr (MODE == 0) {
+      const int bin = score_bin(s);
+      atomicAdd(&S.hist[(c * kBins + bin) >> 1], 1u << ((bin & 1) << 4));
+      if (S.cnt[c] < (unsigned)P.spc) {
+        const unsigned pos = atomicAdd(&S.cnt[c], 1u);
+        if (pos < (unsigned)P.spc) P.g_list[r * kListCap + (size_t)blockIdx.x * P.spc + pos] = key;
+      }
+    } else {
+      const unsigned pos = atomicAdd(&P.g_cnt2[r], 1u);
+      if (pos < (unsigned)kListCap) P.g_list[r * kListCap + pos] = key;
+    }
+  }
+}
+
+template <int MODE, int C>
+__global__ void __launch_bounds__(kScanBlock)
+scan_kernel(const __grid_constant__ ScanParams P) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  float* s_tiles = reinterpret_cast<float*>(s_dyn);                      // 2 x [256][C]
+  ScanShared<MODE, C>& S = *reinterpret_cast<ScanShared<MODE, C>*>(s_dyn + 2 * sizeof(float) * kScanBlock * C);
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ int s_any;
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  if constexpr (MODE == 0) {
+    for (int i = tid; i < C * kBins / 2; i += kScanBlock) S.hist[i] = 0u;
+  }
+  if (tid == 0) s_any = 0;
+  __syncthreads();
+  if (tid < C) {
+    S.cnt[tid] = 0u;
+    if constexpr (MODE == 1) {
+      const size_t r = (size_t)tid * P.batch + b;
+      const bool dense = tid != P.ignore_class && P.g_flag[r] != 0u;
+      S.tb[tid] = dense ? P.g_tbin[r] : 0x7fffffff;
+      if (dense) s_any = 1;
+    }
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (MODE == 1 && !s_any) return;                      // no dense segment in this image
+
+  const int A0 = blockIdx.x * P.chunk, A1 = min(A0 + P.chunk, P.L.n_total);
+  unsigned phase0 = 0, phase1 = 0;
+  for (int l = 0; l < P.L.n_layers; ++l) {
+    const int lo = max(A0, P.L.offset[l]), hi = min(A1, P.L.offset[l + 1]);
+    if (lo >= hi) continue;
+    // row(n) = slab + n * C for the global anchor index n
+    const float* slab = P.probs.base[l] + (long long)b * P.probs.stride[l] - (long long)P.L.offset[l] * C;
+    // bulk copies need 16 B aligned sources: peel up to 3 head anchors (C odd: 4C*h covers every residue)
+    int head = 0;
+    while (head < 4 && ((reinterpret_cast<uintptr_t>(slab + (long long)(lo + head) * C)) & 15u) != 0) ++head;
+    int t0 = lo + head, t1 = hi;
+    if (head == 4 || t0 >= hi) { t0 = hi; t1 = hi; }
+    t1 = t0 + ((t1 - t0) & ~3);                          // whole multiples of 4 anchors = 16 B multiples
+    // ---- TMA tiles of 256 anchors, double buffered: start the first copy, then do the scalar anchors
+    const int ntiles = (t1 - t0 + kScanBlock - 1) / kScanBlock;
+    if (ntiles > 0 && tid == 0) {
+      const int cnt = min(kScanBlock, t1 - t0);
+      tma_load_1d(s_tiles, slab + (long long)t0 * C, (unsigned)(cnt * C * 4), &s_bar[0]);
+    }
+    // ---- scalar anchors: [lo, t0) and [t1, hi), at most a handful, straight from global memory
+    const int nscalar = (t0 - lo) + (hi - t1);
+    for (int i = tid; i < nscalar; i += kScanBlock) {
+      const int n = i < t0 - lo ? lo + i : t1 + (i - (t0 - lo));
+      scan_anchor<MODE, C>(P, S, true, slab + (long long)n * C, n, b);
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const int a0 = t0 + t * kScanBlock;
+      const int cnt = min(kScanBlock, t1 - a0);
+      if (t + 1 < ntiles && tid == 0) {
+        const int a1 = a0 + kScanBlock;
+        const int c1 = min(kScanBlock, t1 - a1);
+        tma_load_1d(s_tiles + (buf ^ 1) * kScanBlock * C, slab + (long long)a1 * C, (unsigned)(c1 * C * 4),
+                    &s_bar[buf ^ 1]);
+      }
+      mbar_wait(&s_bar[buf], buf ? phase1 : phase0);
+      if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+      // row stride C words: conflict-free across lanes for odd C
+      scan_anchor<MODE, C>(P, S, tid < cnt, s_tiles + buf * kScanBlock * C + tid * C, a0 + tid, b);
+      __syncthreads();                                   // tile consumed: its buffer may be refilled
+    }
+  }
+  if constexpr (MODE == 0) {
+    __syncthreads();
+    if (tid < C) {
+      const size_t r = (size_t)tid * P.batch + b;
+      const unsigned c = S.cnt[tid];
+      P.g_cnt1[r * kMaxChunks + blockIdx.x] = c < (unsigned)P.spc ? c : (unsigned)P.spc;
+      if (c >= (unsigned)P.spc) P.g_flag[r] = 1u;        // out of slots (conservatively also when exactly full)
+    }
+    for (int i = tid; i < C * kBins / 2; i += kScanBlock) {
+      const unsigned w = S.hist[i];
+      if (w) {
+        const int c = (2 * i) / kBins, bin = 2 * i - c * kBins;
+        unsigned* g = P.g_hist + ((size_t)c * P.batch + b) * kBins + bin;
+        if (w & 0xffffu) atomicAdd(g, w & 0xffffu);
+        if (w >> 16) atomicAdd(g + 1, w >> 16);
+      }
+    }
+  }
+}
+
 // one warp per segment: the smallest bin t with count(bins >= t) >= k  (0 when fewer than k candidates)
 __global__ void __launch_bounds__(256)
 thresh_kernel(const unsigned* __restrict__ g_hist, int rows, int k, int* __restrict__ tbin) {
@@ -177,6 +368,13 @@ struct SegParams {
   int has_loc, batch, ignore_class, cap, k, keep;
   float nms_thr;
   const float* clip;
+  // candidate lists: [rows][list_cap]; a segment reads cnt2 entries when dense, else cnt1
+  const unsigned* cnt1;
+  const unsigned* cnt2;
+  const unsigned* flag;
+  const int* tbin;
+  unsigned* over;            // out: 1 when the segment must be redone by the exact general kernels
+  int list_cap, force_dense, chunks, spc;
 };
 
 // bytes of the aliased region: sort keys, later {kept boxes, overlap words, batch rows, kept areas}
@@ -201,8 +399,7 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float den, float thr) {
 }
 
 __global__ void __launch_bounds__(kSegBlock)
-segment_kernel(const __grid_constant__ SegParams P, const unsigned* __restrict__ g_cnt,
-               const unsigned long long* __restrict__ g_list, float* __restrict__ out_scores,
+segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __restrict__ g_list, float* __restrict__ out_scores,
                float* __restrict__ out_boxes, int32_t* __restrict__ out_counts) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   // region A: sort keys (cap x 8 B); after the gather it is re-used for the NMS working set
@@ -222,22 +419,46 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned* __restrict__
   float* s_score = s_area + k;
   int* s_selected = reinterpret_cast<int*>(s_score + k);
   __shared__ unsigned long long s_dead, s_sel;
-  __shared__ int s_nsel;
+  __shared__ int s_nsel, s_n;
 
   const long long r = blockIdx.x;
   const int c = (int)(r / P.batch), b = (int)(r % P.batch);
   if (c == P.ignore_class) return;
-  const unsigned cnt_raw = g_cnt[r];
-  if (cnt_raw > (unsigned)cap) return;               // overflow: handled by the general kernels
-  const int cnt = (int)cnt_raw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool dense = P.force_dense || P.flag[r] != 0u;
+  if (dense && P.cnt2[r] > (unsigned)P.list_cap) {    // list truncated: exact general kernels take over
+    if (tid == 0) P.over[r] = 1u;
+    return;
+  }
+  // ---- 0. load the list, keeping entries at or above the threshold bin (count(bins >= tbin) >= k)
+  const int tb = P.tbin[r];
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  const int nparts = dense ? 1 : P.chunks;
+  for (int part = 0; part < nparts; ++part) {
+    const unsigned n_in = dense ? P.cnt2[r] : P.cnt1[r * kMaxChunks + part];
+    const unsigned long long* src = g_list + r * P.list_cap + (size_t)part * P.spc;
+    for (unsigned j = tid; j < n_in; j += kSegBlock) {
+      const unsigned long long e = src[j];
+      if (score_bin(__uint_as_float((unsigned)(e >> 32))) >= tb) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < cap) s_keys[pos] = e;
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = s_n;
+  if (cnt > cap) {                                    // massive ties in the threshold bin
+    if (tid == 0) P.over[r] = 1u;
+    return;
+  }
 
   // ---- 1. sort the candidate list: descending (score bits, ~anchor).  Bitonic network; every
   // compare-exchange with stride < 32 runs in registers with warp shuffles (one element per lane),
   // only strides >= 32 go through shared memory.
   int n2 = 32;
   while (n2 < cnt) n2 <<= 1;
-  for (int j = tid; j < n2; j += kSegBlock) s_keys[j] = j < cnt ? g_list[r * cap + j] : 0ull;
+  for (int j = cnt + tid; j < n2; j += kSegBlock) s_keys[j] = 0ull;
   __syncthreads();
   for (int g = warp; g < (n2 >> 5); g += kSegWarps) {            // sizes 2..32 entirely in registers
     const int e = (g << 5) + lane;
@@ -441,50 +662,88 @@ static int stream_cap(int k) {
   return p * 2 < 1024 ? 1024 : p * 2;
 }
 
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
 size_t stream_workspace_bytes(int batch, int n_classes, int top_k) {
+  (void)top_k;
   const size_t rows = (size_t)batch * n_classes;
-  const int cap = stream_cap(top_k);
-  return rows * kBins * 4 + rows * 4 /*cnt*/ + 256 + rows * 4 /*tbin*/ + 256 + rows * (size_t)cap * 8 + 256;
+  return align256(rows * kBins * 4 + rows * 4 * 3) + align256(rows * 4) + align256(rows * kMaxChunks * 4) +
+         align256(rows * (size_t)kListCap * 8) + 256;
 }
 
-// Returns ROD_OK after enqueueing A1, T, A2, B.  g_cnt (device, [rows]) tells the caller's
-// fallback kernels which segments overflowed (cnt > cap).
+// Enqueues A1, T, A2, B.  *over_out (device, [rows]) is non-zero for segments the exact general
+// kernels must redo.
 int launch_detect_stream(const Layout& L, const float* anchors_center, const LayeredF& probs, const LayeredF* loc,
                          const LayeredF* refine, const LayeredF* det, int batch, int C, int ignore_class,
                          float select_thr, float nms_thr, int top_k, int keep, const float* clip, float* out_scores,
-                         float* out_boxes, int32_t* out_counts, void* ws, const unsigned** cnt_out, int* cap_out,
+                         float* out_boxes, int32_t* out_counts, void* ws, const unsigned** over_out, int* cap_out,
                          cudaStream_t st) {
   const size_t rows = (size_t)batch * C;
   const int cap = stream_cap(top_k);
   unsigned char* p = reinterpret_cast<unsigned char*>(ws);
   unsigned* g_hist = reinterpret_cast<unsigned*>(p);
-  unsigned* g_cnt = g_hist + rows * kBins;
-  size_t zero_bytes = rows * kBins * 4 + rows * 4;
-  p += ((zero_bytes + 255) / 256) * 256;
+  unsigned* g_cnt2 = g_hist + rows * kBins;
+  unsigned* g_flag = g_cnt2 + rows;
+  unsigned* g_over = g_flag + rows;
+  const size_t zero_bytes = rows * kBins * 4 + rows * 4 * 3;
+  p += align256(zero_bytes);
   int* g_tbin = reinterpret_cast<int*>(p);
-  p += ((rows * 4 + 255) / 256) * 256;
+  p += align256(rows * 4);
+  unsigned* g_cnt1 = reinterpret_cast<unsigned*>(p);           // [rows][kMaxChunks], fully written by A1
+  p += align256(rows * kMaxChunks * 4);
   unsigned long long* g_list = reinterpret_cast<unsigned long long*>(p);
   ROD_CUDA(cudaMemsetAsync(g_hist, 0, zero_bytes, st));
   if (out_counts) ROD_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * rows, st));
 
-  StreamParams SP;
-  SP.probs = probs; SP.L = L; SP.C = C; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;
-  const int total_f = L.n_total * C;
-  int chunks = (4 * sm_count() + batch - 1) / batch;           // >= ~4 CTAs per SM in total
-  chunks = chunks < 4 ? 4 : (chunks > 64 ? 64 : chunks);
-  int chunk = (total_f + chunks - 1) / chunks;
-  chunk = ((chunk + 1023) / 1024) * 1024;
-  chunks = (total_f + chunk - 1) / chunk;
-  SP.chunk = chunk;
-  const dim3 grid(chunks, batch);
-  const size_t hsmem = (size_t)C * kBins * 4;
-  ROD_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-  hist_kernel<<<grid, kStreamBlock, hsmem, st>>>(SP, g_hist);
-  ROD_LAUNCH_CHECK("hist_kernel");
-  thresh_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g_hist, (int)rows, top_k, g_tbin);
-  ROD_LAUNCH_CHECK("thresh_kernel");
-  collect_kernel<<<grid, kStreamBlock, 0, st>>>(SP, g_tbin, g_cnt, g_list, cap);
-  ROD_LAUNCH_CHECK("collect_kernel");
+  int force_dense = 0, n_chunks = 1, spc = kListCap;
+  if (C == 11) {
+    // ---- TMA-staged single pass (+ dense second pass)
+    ScanParams SP;
+    SP.probs = probs; SP.L = L; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;
+    SP.g_hist = g_hist; SP.g_cnt1 = g_cnt1; SP.g_cnt2 = g_cnt2; SP.g_flag = g_flag; SP.g_tbin = g_tbin; SP.g_list = g_list;
+    int chunks = (4 * sm_count() + batch - 1) / batch;          // ~4 CTAs per SM in total
+    chunks = chunks < 2 ? 2 : (chunks > 64 ? 64 : chunks);
+    int chunk = (L.n_total + chunks - 1) / chunks;
+    chunk = ((chunk + kScanBlock - 1) / kScanBlock) * kScanBlock;
+    if (chunk > 61440) chunk = 61440;                           // 16-bit packed histogram counters per CTA
+    chunks = (L.n_total + chunk - 1) / chunk;
+    ROD_REQUIRE(chunks <= kMaxChunks, "rod_detect: %d anchors need more than %d CTAs per image", L.n_total, kMaxChunks);
+    SP.chunk = chunk;
+    SP.chunks = n_chunks = chunks;
+    SP.spc = spc = kListCap / chunks;
+    const dim3 grid(chunks, batch);
+    const size_t tile_bytes = 2 * sizeof(float) * kScanBlock * 11;
+    const size_t smem0 = tile_bytes + sizeof(ScanShared<0, 11>), smem1 = tile_bytes + sizeof(ScanShared<1, 11>);
+    ROD_CUDA(cudaFuncSetAttribute(scan_kernel<0, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+    scan_kernel<0, 11><<<grid, kScanBlock, smem0, st>>>(SP);
+    ROD_LAUNCH_CHECK("scan_kernel<0>");
+    thresh_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g_hist, (int)rows, top_k, g_tbin);
+    ROD_LAUNCH_CHECK("thresh_kernel");
+    scan_kernel<1, 11><<<grid, kScanBlock, smem1, st>>>(SP);
+    ROD_LAUNCH_CHECK("scan_kernel<1>");
+  } else {
+    // ---- generic prediction depth: plain-load two-pass kernels, every segment takes the dense route
+    force_dense = 1;
+    StreamParams SP;
+    SP.probs = probs; SP.L = L; SP.C = C; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;
+    const int total_f = L.n_total * C;
+    int chunks = (4 * sm_count() + batch - 1) / batch;
+    chunks = chunks < 4 ? 4 : (chunks > 64 ? 64 : chunks);
+    int chunk = (total_f + chunks - 1) / chunks;
+    chunk = ((chunk + 1023) / 1024) * 1024;
+    chunks = (total_f + chunk - 1) / chunk;
+    SP.chunk = chunk;
+    const dim3 grid(chunks, batch);
+    const size_t hsmem = (size_t)C * kBins * 4;
+    ROD_REQUIRE(hsmem <= 200 * 1024, "rod_detect: %d classes need %zu B of shared memory for the histogram", C, hsmem);
+    ROD_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+    hist_kernel<<<grid, kStreamBlock, hsmem, st>>>(SP, g_hist);
+    ROD_LAUNCH_CHECK("hist_kernel");
+    thresh_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g_hist, (int)rows, top_k, g_tbin);
+    ROD_LAUNCH_CHECK("thresh_kernel");
+    collect_kernel<<<grid, kStreamBlock, 0, st>>>(SP, g_tbin, g_cnt2, g_list, kListCap);
+    ROD_LAUNCH_CHECK("collect_kernel");
+  }
 
   SegParams G;
   G.has_loc = loc ? 1 : 0;
@@ -494,13 +753,15 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   G.center = anchors_center;
   G.L = L; G.batch = batch; G.ignore_class = ignore_class; G.cap = cap; G.k = top_k; G.keep = keep;
   G.nms_thr = nms_thr; G.clip = clip;
+  G.cnt1 = g_cnt1; G.cnt2 = g_cnt2; G.flag = g_flag; G.tbin = g_tbin; G.over = g_over;
+  G.list_cap = kListCap; G.force_dense = force_dense; G.chunks = n_chunks; G.spc = spc;
   const size_t smem = seg_smem_bytes(cap, top_k, keep);
   ROD_REQUIRE(smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep, smem);
   ROD_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  segment_kernel<<<(unsigned)rows, kSegBlock, smem, st>>>(G, g_cnt, g_list, out_scores, out_boxes, out_counts);
+  segment_kernel<<<(unsigned)rows, kSegBlock, smem, st>>>(G, g_list, out_scores, out_boxes, out_counts);
   ROD_LAUNCH_CHECK("segment_kernel");
-  *cnt_out = g_cnt;
-  *cap_out = cap;
+  *over_out = g_over;
+  *cap_out = 0;                                                 // fallback kernels run where over[r] > 0
   return ROD_OK;
 }
 

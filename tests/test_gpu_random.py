@@ -239,3 +239,25 @@ def test_detect_fewer_candidates_than_topk(env):
         assert bit_equal(rs[c].cpu().numpy(), o_s[c]) and bit_equal(rb[c].cpu().numpy(), o_b[c]), c
         n += int((o_s[c] != 0).sum())
     assert n > 0 and not rs[4][0].any()
+
+
+def test_detect_generic_class_count(env, monkeypatch):
+    """Prediction depth != 11 takes the plain-load two-pass kernels (no TMA tiles)."""
+    layout, B, C = "418", 2, 6
+    table = env.otable[layout]
+    rng = np.random.default_rng(77)
+    z = (rng.standard_normal(size=(B, table.n, C)) * 3.0).astype(np.float32)
+    z[..., 0] += np.float32(2.0)
+    z -= z.max(-1, keepdims=True)
+    probs = (np.exp(z) / np.exp(z).sum(-1, keepdims=True)).astype(np.float32)
+    ro = np.stack([env.synth.head_offsets(600 + b, table.n) for b in range(B)])
+    do = np.stack([env.synth.head_offsets(600 + b, table.n, 1) for b in range(B)])
+    preds = to_cuda_list(probs, table.shapes, (C,), env.dev)
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+    monkeypatch.setattr(env.config, "total_obj_n", C)
+    rs, rb = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=0.3,
+                                           nms_threshold=0.45, top_k=400, keep_top_k=200)
+    o_s, o_b = R.detected_bboxes(probs, R.decode_corner(table, ro, do), 0.3, 0.45, None, 400, 200, num_classes=C)
+    assert sorted(rs.keys()) == list(range(1, C))
+    for c in range(1, C):
+        assert bit_equal(rs[c].cpu().numpy(), o_s[c]) and bit_equal(rb[c].cpu().numpy(), o_b[c]), c
