@@ -27,7 +27,7 @@ namespace rod {
 
 constexpr int kBins = 1024;
 constexpr int kStreamBlock = 256;
-constexpr int kSegBlock = 128;
+constexpr int kSegBlock = 256;
 constexpr int kSegWarps = kSegBlock / 32;
 
 __device__ __forceinline__ int score_bin(float s) {
@@ -143,6 +143,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   } while (!ok);
 }
 
+__device__ __forceinline__ int warp_threshold_bin(const unsigned* __restrict__ hist_row, int k, int lane);
+
 struct ScanParams {
   LayeredF probs;
   Layout L;
@@ -153,8 +155,9 @@ struct ScanParams {
   unsigned* g_cnt1;                    // [rows][kMaxChunks] candidates written by each sparse-pass CTA
   unsigned* g_cnt2;                    // [rows] candidates appended by the dense pass
   unsigned* g_flag;                    // [rows] != 0: some CTA ran out of list slots => dense segment
-  const int* g_tbin;                   // [rows] (MODE 1)
-  unsigned long long* g_list;          // [rows][kListCap]
+  unsigned long long* g_list;          // [rows][kListCap]  sparse-pass slices
+  unsigned long long* g_list2;         // [rows][cap2]      entries at or above the threshold bin
+  int cap2, top_k;
 };
 
 template <int MODE, int C>
@@ -197,7 +200,7 @@ __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE
       }
     } else {
       const unsigned pos = atomicAdd(&P.g_cnt2[r], 1u);
-      if (pos < (unsigned)kListCap) P.g_list[r * kListCap + pos] = key;
+      if (pos < (unsigned)P.cap2) P.g_list2[r * P.cap2 + pos] = key;
     }
   }
 }
@@ -218,13 +221,17 @@ scan_kernel(const __grid_constant__ ScanParams P) {
   }
   if (tid == 0) s_any = 0;
   __syncthreads();
-  if (tid < C) {
-    S.cnt[tid] = 0u;
-    if constexpr (MODE == 1) {
-      const size_t r = (size_t)tid * P.batch + b;
-      const bool dense = tid != P.ignore_class && P.g_flag[r] != 0u;
-      S.tb[tid] = dense ? P.g_tbin[r] : 0x7fffffff;
-      if (dense) s_any = 1;
+  if (tid < C) S.cnt[tid] = 0u;
+  if constexpr (MODE == 1) {
+    // threshold bins of this image's dense classes, straight from the finished histograms
+    for (int c = tid >> 5; c < C; c += kScanBlock / 32) {
+      const size_t r = (size_t)c * P.batch + b;
+      const bool dense = c != P.ignore_class && P.g_flag[r] != 0u;            // warp-uniform
+      const int t = dense ? warp_threshold_bin(P.g_hist + r * kBins, P.top_k, tid & 31) : 0x7fffffff;
+      if ((tid & 31) == 0) {
+        S.tb[c] = t;
+        if (dense) s_any = 1;
+      }
     }
   }
   if (tid == 0) {
@@ -295,6 +302,42 @@ scan_kernel(const __grid_constant__ ScanParams P) {
       }
     }
   }
+}
+
+// smallest bin t with count(bins >= t) >= k (0 when the row holds fewer than k); whole warp, uniform result
+__device__ __forceinline__ int warp_threshold_bin(const unsigned* __restrict__ hist_row, int k, int lane) {
+  const uint4* h = reinterpret_cast<const uint4*>(hist_row + lane * 32);
+  unsigned v[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 x = h[q];
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+  unsigned sum = 0;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) sum += v[q];
+  unsigned suf = sum;                                 // inclusive suffix sum (lane 31 owns the top bins)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += x;
+  }
+  const unsigned above = suf - sum;
+  const unsigned total = __shfl_sync(0xffffffffu, suf, 0);
+  int t = 0;
+  if (total >= (unsigned)k && above < (unsigned)k && suf >= (unsigned)k) {
+    unsigned acc = above;
+    t = lane * 32;
+#pragma unroll
+    for (int q = 31; q >= 0; --q) {
+      acc += v[q];
+      if (acc >= (unsigned)k) { t = lane * 32 + q; break; }
+    }
+  }
+  // exactly one lane found it (or none when total < k): max-reduce
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+  return t;
 }
 
 // one warp per segment: the smallest bin t with count(bins >= t) >= k  (0 when fewer than k candidates)
@@ -368,18 +411,21 @@ struct SegParams {
   int has_loc, batch, ignore_class, cap, k, keep;
   float nms_thr;
   const float* clip;
-  // candidate lists: [rows][list_cap]; a segment reads cnt2 entries when dense, else cnt1
+  // sparse segments: per-CTA slices of the scan pass ([rows][kListCap], counts [rows][kMaxChunks]),
+  // filtered here against the threshold bin derived from the histogram row;
+  // dense segments (flag != 0 or force_dense): the final list the second pass wrote ([rows][cap], cnt2)
+  const unsigned long long* list1;
   const unsigned* cnt1;
-  const unsigned* cnt2;
+  const unsigned* hist;
   const unsigned* flag;
-  const int* tbin;
+  const unsigned* cnt2;
   unsigned* over;            // out: 1 when the segment must be redone by the exact general kernels
-  int list_cap, force_dense, chunks, spc;
+  int chunks, spc, force_dense;
 };
 
 // bytes of the aliased region: sort keys, later {kept boxes, overlap words, batch rows, kept areas}
 __host__ __device__ inline size_t seg_region_a(int cap, int keep) {
-  const size_t a = (size_t)cap * 8, b = (size_t)keep * (16 + 8 + 4) + 128 * 8;
+  const size_t a = (size_t)cap * 16 + 1024 * 4, b = (size_t)keep * (16 + 8 + 4) + 128 * 8;
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
@@ -398,7 +444,7 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float den, float thr) {
   return __fdiv_rn(inter, den) > thr;
 }
 
-__global__ void __launch_bounds__(kSegBlock)
+__global__ void __launch_bounds__(kSegBlock, 5)
 segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __restrict__ g_list, float* __restrict__ out_scores,
                float* __restrict__ out_boxes, int32_t* __restrict__ out_counts) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -419,73 +465,123 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   float* s_score = s_area + k;
   int* s_selected = reinterpret_cast<int*>(s_score + k);
   __shared__ unsigned long long s_dead, s_sel;
-  __shared__ int s_nsel, s_n;
+  __shared__ int s_nsel;
 
   const long long r = blockIdx.x;
   const int c = (int)(r / P.batch), b = (int)(r % P.batch);
   if (c == P.ignore_class) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- 0. candidates at or above the threshold bin -> s_keys[0, cnt)
+  __shared__ int s_n, s_tbv;
+  __shared__ unsigned s_part[kMaxChunks];
   const bool dense = P.force_dense || P.flag[r] != 0u;
-  if (dense && P.cnt2[r] > (unsigned)P.list_cap) {    // list truncated: exact general kernels take over
-    if (tid == 0) P.over[r] = 1u;
-    return;
-  }
-  // ---- 0. load the list, keeping entries at or above the threshold bin (count(bins >= tbin) >= k)
-  const int tb = P.tbin[r];
-  if (tid == 0) s_n = 0;
-  __syncthreads();
-  const int nparts = dense ? 1 : P.chunks;
-  for (int part = 0; part < nparts; ++part) {
-    const unsigned n_in = dense ? P.cnt2[r] : P.cnt1[r * kMaxChunks + part];
-    const unsigned long long* src = g_list + r * P.list_cap + (size_t)part * P.spc;
-    for (unsigned j = tid; j < n_in; j += kSegBlock) {
-      const unsigned long long e = src[j];
-      if (score_bin(__uint_as_float((unsigned)(e >> 32))) >= tb) {
-        const int pos = atomicAdd(&s_n, 1);
-        if (pos < cap) s_keys[pos] = e;
+  int cnt;
+  if (dense) {                                        // already filtered by the second pass
+    const unsigned n_in = P.cnt2[r];
+    if (n_in > (unsigned)cap) {                       // massive ties in the threshold bin: exact kernels redo it
+      if (tid == 0) P.over[r] = 1u;
+      return;
+    }
+    cnt = (int)n_in;
+    for (int j = tid; j < cnt; j += kSegBlock) s_keys[j] = g_list[r * cap + j];
+  } else {
+    if (tid < P.chunks) s_part[tid] = P.cnt1[r * kMaxChunks + tid];
+    if (tid == 0) s_n = 0;
+    if (warp == kSegWarps - 1) {                      // smallest bin with count(bins >= t) >= k
+      const int t = warp_threshold_bin(P.hist + r * kBins, k, lane);
+      if (lane == 0) s_tbv = t;
+    }
+    __syncthreads();
+    const int tb = s_tbv;
+    const unsigned long long* base = P.list1 + r * kListCap;
+    // four slices (<= 512 entries each, two per thread) per round: 8 independent loads in flight
+    for (int p0 = 0; p0 < P.chunks; p0 += 4) {
+      unsigned long long ev[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int part = p0 + (u >> 1);
+        const unsigned j = (u & 1) * kSegBlock + tid;
+        ev[u] = (part < P.chunks && j < s_part[part]) ? base[(size_t)part * P.spc + j] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        // empty slots are 0 (score +0.0 -> bin 0, anchor ~0): real entries have score >= thr > 0
+        if ((unsigned)(ev[u] >> 32) != 0u && score_bin(__uint_as_float((unsigned)(ev[u] >> 32))) >= tb) {
+          const int pos = atomicAdd(&s_n, 1);
+          if (pos < cap) s_keys[pos] = ev[u];
+        }
       }
     }
-  }
-  __syncthreads();
-  const int cnt = s_n;
-  if (cnt > cap) {                                    // massive ties in the threshold bin
-    if (tid == 0) P.over[r] = 1u;
-    return;
+    __syncthreads();
+    cnt = s_n;
+    if (cnt > cap) {                                  // massive ties in the threshold bin
+      if (tid == 0) P.over[r] = 1u;
+      return;
+    }
   }
 
-  // ---- 1. sort the candidate list: descending (score bits, ~anchor).  Bitonic network; every
-  // compare-exchange with stride < 32 runs in registers with warp shuffles (one element per lane),
-  // only strides >= 32 go through shared memory.
-  int n2 = 32;
-  while (n2 < cnt) n2 <<= 1;
-  for (int j = cnt + tid; j < n2; j += kSegBlock) s_keys[j] = 0ull;
-  __syncthreads();
-  for (int g = warp; g < (n2 >> 5); g += kSegWarps) {            // sizes 2..32 entirely in registers
-    const int e = (g << 5) + lane;
-    unsigned long long v = s_keys[e];
+  // ---- 1. sort the candidate list: descending (score bits, ~anchor) = tf.nn.top_k order.
+  // Counting sort on the 1024 score bins the histogram pass already uses (monotone in the score),
+  // then an exact rank inside each bin (bins hold a handful of entries; all-tied inputs stay
+  // correct, just slower).  Four block-wide steps instead of a 45-step bitonic network.
+  {
+    constexpr int kPer = (2 * ROD_MAX_TOPK + kSegBlock - 1) / kSegBlock;   // list entries per thread (cap <= 2048)
+    unsigned long long* s_tmp = s_keys + cap;
+    unsigned* s_h = reinterpret_cast<unsigned*>(s_keys + 2 * cap);        // [kBins]
+    __shared__ unsigned s_wsum[kSegWarps];
+    for (int i = tid; i < kBins; i += kSegBlock) s_h[i] = 0u;
+    __syncthreads();
+    unsigned long long ev[kPer];
+    int ebin[kPer];
+    unsigned erk[kPer];
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1)
-#pragma unroll
-      for (int stride = size >> 1; stride > 0; stride >>= 1) v = bitonic_cx(v, e, lane, size, stride);
-    s_keys[e] = v;
-  }
-  __syncthreads();
-  for (int size = 64; size <= n2; size <<= 1) {
-    for (int stride = size >> 1; stride >= 32; stride >>= 1) {
-      for (int t = tid; t < (n2 >> 1); t += kSegBlock) {
-        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = s_keys[lo], x = s_keys[hi];
-        if ((a < x) == desc) { s_keys[lo] = x; s_keys[hi] = a; }
+    for (int q = 0; q < kPer; ++q) {
+      const int j = tid + q * kSegBlock;
+      if (j < cnt) {
+        ev[q] = s_keys[j];
+        ebin[q] = score_bin(__uint_as_float((unsigned)(ev[q] >> 32)));
+        erk[q] = atomicAdd(&s_h[ebin[q]], 1u);
       }
-      __syncthreads();
     }
-    for (int g = warp; g < (n2 >> 5); g += kSegWarps) {
-      const int e = (g << 5) + lane;
-      unsigned long long v = s_keys[e];
+    __syncthreads();
+    // exclusive suffix sum over bins (higher bins first): thread t owns bins [4t, 4t+4)
+    {
+      static_assert(kBins == 4 * kSegBlock, "one thread per four bins");
+      const unsigned h0 = s_h[4 * tid], h1 = s_h[4 * tid + 1], h2 = s_h[4 * tid + 2], h3 = s_h[4 * tid + 3];
+      const unsigned mine = h0 + h1 + h2 + h3;
+      unsigned suf = mine;                             // inclusive suffix over the warp's higher lanes
 #pragma unroll
-      for (int stride = 16; stride > 0; stride >>= 1) v = bitonic_cx(v, e, lane, size, stride);
-      s_keys[e] = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += x;
+      }
+      if (lane == 0) s_wsum[warp] = suf;
+      __syncthreads();
+      unsigned above = suf - mine;
+      for (int w = warp + 1; w < kSegWarps; ++w) above += s_wsum[w];
+      s_h[4 * tid + 3] = above;                        // start offset of every bin in the sorted order
+      s_h[4 * tid + 2] = above + h3;
+      s_h[4 * tid + 1] = above + h3 + h2;
+      s_h[4 * tid] = above + h3 + h2 + h1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int j = tid + q * kSegBlock;
+      if (j < cnt) s_tmp[s_h[ebin[q]] + erk[q]] = ev[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int j = tid + q * kSegBlock;
+      if (j < cnt) {
+        const unsigned long long e = s_tmp[j];
+        const int bin = score_bin(__uint_as_float((unsigned)(e >> 32)));
+        const int s0 = (int)s_h[bin], s1 = bin > 0 ? (int)s_h[bin - 1] : cnt;
+        int rank = 0;
+        for (int x = s0; x < s1; ++x) rank += (s_tmp[x] > e) ? 1 : 0;
+        s_keys[s0 + rank] = e;
+      }
     }
     __syncthreads();
   }
@@ -555,16 +651,17 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     if (tid == 0) s_dead = 0ull;
     if (tid < 64) s_cm[tid] = 0ull;
     __syncthreads();
-    // (b) exact IoU > thr on the intersecting pairs
-    for (int t = tid; t < nk + nb; t += kSegBlock) {
-      const bool vs_kept = t < nk;
-      unsigned long long maybe = vs_kept ? s_ov[t] : s_bm[t - nk];
+    // (b) exact IoU > thr on the intersecting pairs; two threads per 64-bit word (32 columns each)
+    for (int t = tid; t < 2 * (nk + nb); t += kSegBlock) {
+      const int wd = t >> 1, half = t & 1;
+      const bool vs_kept = wd < nk;
+      unsigned maybe = (unsigned)((vs_kept ? s_ov[wd] : s_bm[wd - nk]) >> (half << 5));
       if (maybe) {
-        const float4 bi = vs_kept ? s_kbox[t] : s_nbox[p0 + t - nk];
-        const float ai = vs_kept ? s_karea[t] : s_area[p0 + t - nk];
+        const float4 bi = vs_kept ? s_kbox[wd] : s_nbox[p0 + wd - nk];
+        const float ai = vs_kept ? s_karea[wd] : s_area[p0 + wd - nk];
         unsigned long long bits = 0ull;
         while (maybe) {
-          const int q = __ffsll((long long)maybe) - 1;
+          const int q = (__ffs(maybe) - 1) + (half << 5);
           maybe &= maybe - 1;
           const float4 bj = s_nbox[p0 + q];
           const float ih = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
@@ -578,7 +675,7 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
           if (bits) atomicOr(&s_dead, bits);
         } else {
           // column view of the intra-batch suppression relation: s_cm[q] = rows that suppress q
-          const unsigned long long me = 1ull << (t - nk);
+          const unsigned long long me = 1ull << (wd - nk);
           while (bits) {
             const int q = __ffsll((long long)bits) - 1;
             bits &= bits - 1;
@@ -608,7 +705,12 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
         U &= ~(newK | newD);
       }
       const int room = keep - nk;                     // greedy stops once keep boxes are selected
-      while (__popcll(K) > room) K &= ~(1ull << (63 - __clzll((long long)K)));
+      if (__popcll(K) > room) {                       // keep only the first `room` survivors
+        const unsigned lo32 = (unsigned)K, hi32 = (unsigned)(K >> 32);
+        const int cl = __popc(lo32);
+        const int pos = room <= cl ? (int)__fns(lo32, 0u, room) : 32 + (int)__fns(hi32, 0u, room - cl);
+        K &= (pos >= 63) ? ~0ull : ((2ull << pos) - 1ull);
+      }
       if (lane == 0) s_sel = K;
     }
     __syncthreads();
@@ -665,10 +767,9 @@ static int stream_cap(int k) {
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t stream_workspace_bytes(int batch, int n_classes, int top_k) {
-  (void)top_k;
   const size_t rows = (size_t)batch * n_classes;
   return align256(rows * kBins * 4 + rows * 4 * 3) + align256(rows * 4) + align256(rows * kMaxChunks * 4) +
-         align256(rows * (size_t)kListCap * 8) + 256;
+         align256(rows * (size_t)kListCap * 8) + align256(rows * (size_t)stream_cap(top_k) * 8) + 256;
 }
 
 // Enqueues A1, T, A2, B.  *over_out (device, [rows]) is non-zero for segments the exact general
@@ -692,17 +793,20 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   unsigned* g_cnt1 = reinterpret_cast<unsigned*>(p);           // [rows][kMaxChunks], fully written by A1
   p += align256(rows * kMaxChunks * 4);
   unsigned long long* g_list = reinterpret_cast<unsigned long long*>(p);
+  p += align256(rows * (size_t)kListCap * 8);
+  unsigned long long* g_list2 = reinterpret_cast<unsigned long long*>(p);   // [rows][cap]
+  int n_chunks = 1, spc = 512, force_dense = 0;
   ROD_CUDA(cudaMemsetAsync(g_hist, 0, zero_bytes, st));
   if (out_counts) ROD_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * rows, st));
 
-  int force_dense = 0, n_chunks = 1, spc = kListCap;
   if (C == 11) {
     // ---- TMA-staged single pass (+ dense second pass)
     ScanParams SP;
     SP.probs = probs; SP.L = L; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;
-    SP.g_hist = g_hist; SP.g_cnt1 = g_cnt1; SP.g_cnt2 = g_cnt2; SP.g_flag = g_flag; SP.g_tbin = g_tbin; SP.g_list = g_list;
+    SP.g_hist = g_hist; SP.g_cnt1 = g_cnt1; SP.g_cnt2 = g_cnt2; SP.g_flag = g_flag; SP.g_list = g_list;
+    SP.g_list2 = g_list2; SP.cap2 = cap; SP.top_k = top_k;
     int chunks = (4 * sm_count() + batch - 1) / batch;          // ~4 CTAs per SM in total
-    chunks = chunks < 2 ? 2 : (chunks > 64 ? 64 : chunks);
+    chunks = chunks < 8 ? 8 : (chunks > 32 ? 32 : chunks);     // >= 8: list slices of at most 512 entries
     int chunk = (L.n_total + chunks - 1) / chunks;
     chunk = ((chunk + kScanBlock - 1) / kScanBlock) * kScanBlock;
     if (chunk > 61440) chunk = 61440;                           // 16-bit packed histogram counters per CTA
@@ -710,15 +814,13 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     ROD_REQUIRE(chunks <= kMaxChunks, "rod_detect: %d anchors need more than %d CTAs per image", L.n_total, kMaxChunks);
     SP.chunk = chunk;
     SP.chunks = n_chunks = chunks;
-    SP.spc = spc = kListCap / chunks;
+    SP.spc = spc = kListCap / chunks < 512 ? kListCap / chunks : 512;
     const dim3 grid(chunks, batch);
     const size_t tile_bytes = 2 * sizeof(float) * kScanBlock * 11;
     const size_t smem0 = tile_bytes + sizeof(ScanShared<0, 11>), smem1 = tile_bytes + sizeof(ScanShared<1, 11>);
     ROD_CUDA(cudaFuncSetAttribute(scan_kernel<0, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
     scan_kernel<0, 11><<<grid, kScanBlock, smem0, st>>>(SP);
     ROD_LAUNCH_CHECK("scan_kernel<0>");
-    thresh_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g_hist, (int)rows, top_k, g_tbin);
-    ROD_LAUNCH_CHECK("thresh_kernel");
     scan_kernel<1, 11><<<grid, kScanBlock, smem1, st>>>(SP);
     ROD_LAUNCH_CHECK("scan_kernel<1>");
   } else {
@@ -741,7 +843,7 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     ROD_LAUNCH_CHECK("hist_kernel");
     thresh_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g_hist, (int)rows, top_k, g_tbin);
     ROD_LAUNCH_CHECK("thresh_kernel");
-    collect_kernel<<<grid, kStreamBlock, 0, st>>>(SP, g_tbin, g_cnt2, g_list, kListCap);
+    collect_kernel<<<grid, kStreamBlock, 0, st>>>(SP, g_tbin, g_cnt2, g_list2, cap);
     ROD_LAUNCH_CHECK("collect_kernel");
   }
 
@@ -753,12 +855,13 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   G.center = anchors_center;
   G.L = L; G.batch = batch; G.ignore_class = ignore_class; G.cap = cap; G.k = top_k; G.keep = keep;
   G.nms_thr = nms_thr; G.clip = clip;
-  G.cnt1 = g_cnt1; G.cnt2 = g_cnt2; G.flag = g_flag; G.tbin = g_tbin; G.over = g_over;
-  G.list_cap = kListCap; G.force_dense = force_dense; G.chunks = n_chunks; G.spc = spc;
+  G.cnt2 = g_cnt2; G.over = g_over;
+  G.list1 = g_list; G.cnt1 = g_cnt1; G.hist = g_hist; G.flag = g_flag;
+  G.chunks = n_chunks; G.spc = spc; G.force_dense = force_dense;
   const size_t smem = seg_smem_bytes(cap, top_k, keep);
   ROD_REQUIRE(smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep, smem);
   ROD_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  segment_kernel<<<(unsigned)rows, kSegBlock, smem, st>>>(G, g_list, out_scores, out_boxes, out_counts);
+  segment_kernel<<<(unsigned)rows, kSegBlock, smem, st>>>(G, g_list2, out_scores, out_boxes, out_counts);
   ROD_LAUNCH_CHECK("segment_kernel");
   *over_out = g_over;
   *cap_out = 0;                                                 // fallback kernels run where over[r] > 0
