@@ -430,6 +430,7 @@ def main():
 def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_loop, hbm_gbs, N):
     import torch
     import torch.distributed as dist
+    from rodet_b200.dist import allgather_counts
     from rodet_b200.utils import net_tools
     B = args.batch_detect
     n_sets = 2                                      # 2 x 180 MB of inputs > 126 MB L2
@@ -438,7 +439,6 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
         p, ro, do = host_inputs_detect(500_000 + (rank * n_sets + s) * B, B, stress)
         sets.append({"probs": to_dev_list(p, (N_CLASSES,)), "ro": to_dev_list(ro, (4,)), "do": to_dev_list(do, (4,)),
                      "host": (p, ro, do) if s == 0 else None})
-    gather_buf = [torch.empty((N_CLASSES, B), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
 
     def run(s):
         rs, rb, cnt = net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["probs"], select_threshold=SELECT_THR,
@@ -465,7 +465,7 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
         else:
             cnt = run(s)[2]
         if world > 1:                            # NCCL all-gather of per-rank detection counts
-            dist.all_gather(gather_buf, cnt)
+            allgather_counts(cnt, B * world)
 
     steps = max(10, args.steps // 4)
     ms = time_loop(step, steps, max(3, args.warmup // 4))
