@@ -48,7 +48,8 @@ arm_jaccard_bigger_kernel(const __grid_constant__ Layout L, const __grid_constan
     s_area[g] = __fmul_rn(__fsub_rn(gc.z, gc.x), __fsub_rn(gc.w, gc.y));
   }
   // lane owns anchors n0 + lane and n0 + 32 + lane of the warp's 64 (coalesced 512 B rows)
-  const int n0 = blockIdx.x * kArmTile + warp * (32 * kArmPer);
+  // the last tiles hold the big-anchor layers, whose warps keep most GT boxes: start them first
+  const int n0 = (gridDim.x - 1 - blockIdx.x) * kArmTile + warp * (32 * kArmPer);
   int n[kArmPer];
   float4 a[kArmPer];
   float vol_a[kArmPer], best[kArmPer];

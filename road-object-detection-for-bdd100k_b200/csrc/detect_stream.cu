@@ -116,6 +116,7 @@ hist_kernel(const __grid_constant__ StreamParams P, unsigned* __restrict__ g_his
 // TMA-staged scan (prediction depth C known at compile time)
 // ------------------------------------------------------------------------------------------
 constexpr int kScanBlock = 256;     // threads = anchors per tile
+constexpr int kScanStages = 2;      // TMA tiles in flight per CTA (ring of shared-memory buffers; 4 measured slower: fewer CTAs per SM)
 constexpr int kListCap = 4096;      // per segment candidate list entries (8 B each)
 constexpr int kMaxChunks = 64;      // CTAs per image; each owns kListCap / chunks list slots per class
 
@@ -209,9 +210,9 @@ template <int MODE, int C>
 __global__ void __launch_bounds__(kScanBlock)
 scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
-  float* s_tiles = reinterpret_cast<float*>(s_dyn);                      // 2 x [256][C]
-  ScanShared<MODE, C>& S = *reinterpret_cast<ScanShared<MODE, C>*>(s_dyn + 2 * sizeof(float) * kScanBlock * C);
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  float* s_tiles = reinterpret_cast<float*>(s_dyn);                      // kScanStages x [256][C]
+  ScanShared<MODE, C>& S = *reinterpret_cast<ScanShared<MODE, C>*>(s_dyn + kScanStages * sizeof(float) * kScanBlock * C);
+  __shared__ __align__(8) unsigned long long s_bar[kScanStages];
   __shared__ int s_any;
 
   const int tid = threadIdx.x;
@@ -235,15 +236,14 @@ scan_kernel(const __grid_constant__ ScanParams P) {
     }
   }
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    for (int q = 0; q < kScanStages; ++q) mbar_init(&s_bar[q], 1);
     fence_mbar_init();
   }
   __syncthreads();
   if (MODE == 1 && !s_any) return;                      // no dense segment in this image
 
   const int A0 = blockIdx.x * P.chunk, A1 = min(A0 + P.chunk, P.L.n_total);
-  unsigned phase0 = 0, phase1 = 0;
+  unsigned phases = 0;                                 // bit q = parity of barrier q
   for (int l = 0; l < P.L.n_layers; ++l) {
     const int lo = max(A0, P.L.offset[l]), hi = min(A1, P.L.offset[l + 1]);
     if (lo >= hi) continue;
@@ -255,12 +255,17 @@ scan_kernel(const __grid_constant__ ScanParams P) {
     int t0 = lo + head, t1 = hi;
     if (head == 4 || t0 >= hi) { t0 = hi; t1 = hi; }
     t1 = t0 + ((t1 - t0) & ~3);                          // whole multiples of 4 anchors = 16 B multiples
-    // ---- TMA tiles of 256 anchors, double buffered: start the first copy, then do the scalar anchors
+    // ---- TMA tiles of 256 anchors through a ring of kScanStages buffers: start the first copies,
+    //      then do the scalar anchors while they are in flight
     const int ntiles = (t1 - t0 + kScanBlock - 1) / kScanBlock;
-    if (ntiles > 0 && tid == 0) {
-      const int cnt = min(kScanBlock, t1 - t0);
-      tma_load_1d(s_tiles, slab + (long long)t0 * C, (unsigned)(cnt * C * 4), &s_bar[0]);
-    }
+    auto issue_tile = [&](int t) {
+      const int a = t0 + t * kScanBlock;
+      const int q = t % kScanStages;
+      tma_load_1d(s_tiles + q * kScanBlock * C, slab + (long long)a * C, (unsigned)(min(kScanBlock, t1 - a) * C * 4),
+                  &s_bar[q]);
+    };
+    if (tid == 0)
+      for (int t = 0; t < min(ntiles, kScanStages - 1); ++t) issue_tile(t);
     // ---- scalar anchors: [lo, t0) and [t1, hi), at most a handful, straight from global memory
     const int nscalar = (t0 - lo) + (hi - t1);
     for (int i = tid; i < nscalar; i += kScanBlock) {
@@ -268,19 +273,15 @@ scan_kernel(const __grid_constant__ ScanParams P) {
       scan_anchor<MODE, C>(P, S, true, slab + (long long)n * C, n, b);
     }
     for (int t = 0; t < ntiles; ++t) {
-      const int buf = t & 1;
+      const int q = t % kScanStages;
       const int a0 = t0 + t * kScanBlock;
       const int cnt = min(kScanBlock, t1 - a0);
-      if (t + 1 < ntiles && tid == 0) {
-        const int a1 = a0 + kScanBlock;
-        const int c1 = min(kScanBlock, t1 - a1);
-        tma_load_1d(s_tiles + (buf ^ 1) * kScanBlock * C, slab + (long long)a1 * C, (unsigned)(c1 * C * 4),
-                    &s_bar[buf ^ 1]);
-      }
-      mbar_wait(&s_bar[buf], buf ? phase1 : phase0);
-      if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+      // buffer (t-1) % stages was released by the barrier at the end of the previous iteration
+      if (t + kScanStages - 1 < ntiles && tid == 0) issue_tile(t + kScanStages - 1);
+      mbar_wait(&s_bar[q], (phases >> q) & 1u);
+      phases ^= 1u << q;
       // row stride C words: conflict-free across lanes for odd C
-      scan_anchor<MODE, C>(P, S, tid < cnt, s_tiles + buf * kScanBlock * C + tid * C, a0 + tid, b);
+      scan_anchor<MODE, C>(P, S, tid < cnt, s_tiles + q * kScanBlock * C + tid * C, a0 + tid, b);
       __syncthreads();                                   // tile consumed: its buffer may be refilled
     }
   }
@@ -805,7 +806,7 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     SP.probs = probs; SP.L = L; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;
     SP.g_hist = g_hist; SP.g_cnt1 = g_cnt1; SP.g_cnt2 = g_cnt2; SP.g_flag = g_flag; SP.g_list = g_list;
     SP.g_list2 = g_list2; SP.cap2 = cap; SP.top_k = top_k;
-    int chunks = (4 * sm_count() + batch - 1) / batch;          // ~4 CTAs per SM in total
+    int chunks = (4 * sm_count() + batch - 1) / batch;          // one wave of ~4 CTAs per SM (8 per SM measured slower: 32 vs 29 us)
     chunks = chunks < 8 ? 8 : (chunks > 32 ? 32 : chunks);     // >= 8: list slices of at most 512 entries
     int chunk = (L.n_total + chunks - 1) / chunks;
     chunk = ((chunk + kScanBlock - 1) / kScanBlock) * kScanBlock;
@@ -816,9 +817,10 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     SP.chunks = n_chunks = chunks;
     SP.spc = spc = kListCap / chunks < 512 ? kListCap / chunks : 512;
     const dim3 grid(chunks, batch);
-    const size_t tile_bytes = 2 * sizeof(float) * kScanBlock * 11;
+    const size_t tile_bytes = kScanStages * sizeof(float) * kScanBlock * 11;
     const size_t smem0 = tile_bytes + sizeof(ScanShared<0, 11>), smem1 = tile_bytes + sizeof(ScanShared<1, 11>);
     ROD_CUDA(cudaFuncSetAttribute(scan_kernel<0, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+    ROD_CUDA(cudaFuncSetAttribute(scan_kernel<1, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     scan_kernel<0, 11><<<grid, kScanBlock, smem0, st>>>(SP);
     ROD_LAUNCH_CHECK("scan_kernel<0>");
     scan_kernel<1, 11><<<grid, kScanBlock, smem1, st>>>(SP);

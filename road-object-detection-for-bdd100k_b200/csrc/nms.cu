@@ -49,7 +49,7 @@ struct GatherBoxes {       // fused: candidates come sorted from the top-k kerne
 
 template <bool FUSED>
 __global__ void __launch_bounds__(kNmsBlock)
-nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ GatherBoxes gsrc, int n, float thr, int keep, int ignore_class,
+nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ GatherBoxes gsrc, long long rows, int n, float thr, int keep, int ignore_class,
            const float* __restrict__ clip, float* __restrict__ out_scores, float* __restrict__ out_boxes,
            int32_t* __restrict__ out_idx, int32_t* __restrict__ out_counts) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -65,10 +65,12 @@ nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ Gath
   int* s_selected = s_src + n;                                                           // [keep]
   __shared__ int s_last, s_nsel;
 
-  const long long r = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (FUSED && (int)(r / gsrc.batch) == ignore_class) return;
-  if (FUSED && gsrc.over_cnt != nullptr && gsrc.over_cnt[r] <= gsrc.over_cap) return;
+  // persistent over rows (the fused path launches a small grid that usually finds nothing to do)
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+  if (FUSED && (int)(r / gsrc.batch) == ignore_class) continue;
+  if (FUSED && gsrc.over_cnt != nullptr && gsrc.over_cnt[r] <= gsrc.over_cap) continue;
+  __syncthreads();
   if (tid == 0) { s_last = 0; s_nsel = 0; }
   __syncthreads();
 
@@ -203,6 +205,7 @@ nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ Gath
     nonzero = __reduce_add_sync(0xffffffffu, nonzero);
     if (lane == 0 && nonzero) atomicAdd(out_counts + r, nonzero);
   }
+  }  // rows
 }
 
 static size_t nms_smem_bytes(int n, int keep, bool dense) {
@@ -242,7 +245,7 @@ extern "C" int rod_bboxes_nms_batch(const float* scores, const float* bboxes, in
   ROD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DenseBoxes d{scores, bboxes};
   GatherBoxes g{};
-  k<<<(unsigned)rows, kNmsBlock, smem, (cudaStream_t)stream>>>(d, g, n, nms_threshold, keep_top_k, -1, nullptr,
+  k<<<(unsigned)rows, kNmsBlock, smem, (cudaStream_t)stream>>>(d, g, rows, n, nms_threshold, keep_top_k, -1, nullptr,
                                                               out_scores, out_bboxes, out_idx, nullptr);
   ROD_LAUNCH_CHECK("nms_kernel<dense>");
   return ROD_OK;
@@ -339,7 +342,8 @@ extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_cente
   auto k = nms_kernel<true>;
   ROD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DenseBoxes d{};
-  k<<<(unsigned)rows, kNmsBlock, smem, st>>>(d, g, top_k, nms_threshold, keep_top_k, ignore_class, clip_box,
+  const unsigned grid = over_cnt ? (unsigned)(rows < 4 * sm_count() ? rows : 4 * sm_count()) : (unsigned)rows;
+  k<<<grid, kNmsBlock, smem, st>>>(d, g, rows, top_k, nms_threshold, keep_top_k, ignore_class, clip_box,
                                             out_scores, out_bboxes, nullptr, out_counts);
   ROD_LAUNCH_CHECK("nms_kernel<fused>");
   return ROD_OK;

@@ -16,17 +16,20 @@ constexpr int kTopkBlock = 1024;
 
 template <typename Src>
 __global__ void __launch_bounds__(kTopkBlock)
-topk_segment_kernel(const __grid_constant__ Src src, int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
+topk_segment_kernel(const __grid_constant__ Src src, long long rows, int k, float* __restrict__ out_scores,
+                    int32_t* __restrict__ out_idx,
                     const float* __restrict__ gather_boxes, float* __restrict__ out_boxes) {
   __shared__ unsigned s_hist[256];
   __shared__ unsigned long long s_sel[ROD_MAX_TOPK];
   __shared__ int s_warp[kTopkBlock / 32];
   __shared__ unsigned s_bin, s_above, s_gt_count;
 
-  const long long r = blockIdx.x;
-  if (!src.row_active(r)) return;
   const int n = src.size();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // persistent over rows: the fused path launches a small grid that usually finds nothing to do
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+  if (!src.row_active(r)) continue;
+  __syncthreads();
 
   // ---------------- radix select of the k-th largest key
   unsigned prefix = 0, pmask = 0;
@@ -142,11 +145,13 @@ topk_segment_kernel(const __grid_constant__ Src src, int k, float* __restrict__ 
     if (out_idx) out_idx[r * k + j] = real ? i : (i | (int)0x80000000);
     if (out_boxes) st4(out_boxes + 4 * (r * k + j), ldg4(gather_boxes + 4 * (r * n + i)));
   }
+  }  // rows
 }
 
 int launch_topk_selected(const SelectedScores& src, long long rows, int k, float* out_scores, int32_t* out_idx,
                          cudaStream_t st) {
-  topk_segment_kernel<SelectedScores><<<(unsigned)rows, kTopkBlock, 0, st>>>(src, k, out_scores, out_idx, nullptr, nullptr);
+  const unsigned grid = src.over_cnt ? (unsigned)(rows < 2 * sm_count() ? rows : 2 * sm_count()) : (unsigned)rows;
+  topk_segment_kernel<SelectedScores><<<grid, kTopkBlock, 0, st>>>(src, rows, k, out_scores, out_idx, nullptr, nullptr);
   ROD_LAUNCH_CHECK("topk_segment_kernel<SelectedScores>");
   return ROD_OK;
 }
@@ -167,7 +172,7 @@ extern "C" int rod_bboxes_sort(const float* scores, const float* bboxes, int64_t
   if (rows == 0) return ROD_OK;
   DenseScores src{scores, n};
   topk_segment_kernel<DenseScores><<<(unsigned)rows, kTopkBlock, 0, (cudaStream_t)stream>>>(
-      src, top_k, out_scores, out_idx, bboxes, out_bboxes);
+      src, rows, top_k, out_scores, out_idx, bboxes, out_bboxes);
   ROD_LAUNCH_CHECK("topk_segment_kernel<DenseScores>");
   return ROD_OK;
 }
