@@ -387,9 +387,7 @@ def main():
             d.copy_(h, non_blocking=True)
         t = net_tools.refine_groundtruth(table, d_center, d_labels, JB, gt_counts=d_counts)
         o = net_tools.det_groundtruth(d_ro, t[0], t[1], t[2], t[3], table)
-        flat_mask = o[1][0]._base if o[1][0]._base is not None else o[1][0]
-        h_mask.copy_(flat_mask.view(B, N) if flat_mask.numel() == B * N else torch.cat([m.reshape(B, -1) for m in o[1]], 1),
-                     non_blocking=True)
+        h_mask.copy_(o[1].flat, non_blocking=True)         # ODM positive mask, flat [B,N]
         torch.cuda.current_stream(dev).synchronize()       # the caller reads the result
 
     e2e_steps = max(5, min(args.steps, 50))
@@ -498,10 +496,8 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
         rs, rb, cnt = net_tools.decode_detected_bboxes(table, d_ro, d_do, d_p, select_threshold=SELECT_THR,
                                                        nms_threshold=NMS_THR, top_k=TOP_K, keep_top_k=KEEP,
                                                        return_counts=True)
-        h_s[1:].copy_(rs[1]._base[1:] if rs[1]._base is not None else torch.stack([rs[c] for c in range(1, N_CLASSES)]),
-                      non_blocking=True)
-        h_b[1:].copy_(rb[1]._base[1:] if rb[1]._base is not None else torch.stack([rb[c] for c in range(1, N_CLASSES)]),
-                      non_blocking=True)
+        h_s[1:].copy_(rs[1]._base[1:], non_blocking=True)   # class-major [C,B,keep] buffers behind the dicts
+        h_b[1:].copy_(rb[1]._base[1:], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
     e2e_steps = max(3, min(steps, 10))

@@ -226,6 +226,11 @@ int rod_l2_flush(void* buf, size_t bytes, void* stream);
  * rank/shape and contiguity are validated here (ROD_E_DLPACK on mismatch).
  * Per-layer lists are host arrays of n_layers `DLTensor*`. */
 struct DLTensor;
+/* Fills a rod_layered_t from a host array of n_layers borrowed DLTensors [B, ..., inner]
+ * (validated: CUDA device, dtype (code,bits), per-image element count, contiguity after the batch
+ * dim, 16-byte alignment for inner == 4).  *batch: in = expected batch or -1, out = batch found. */
+int rod_dl_layered(const rod_layout_t* layout, const struct DLTensor* const* tensors, int inner,
+                   int dtype_code, int dtype_bits, rod_layered_t* out, int* batch);
 int rod_dl_arm_match_encode(const rod_layout_t* layout, const struct DLTensor* anchors_corner,
                             const struct DLTensor* anchors_center, const float* thresholds,
                             const struct DLTensor* center_bboxes, const struct DLTensor* labels,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "rod_detect": (_i, [_LP, _vp, _YP, _YP, _YP, _YP, _i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_peak_fp32_nofma": (_i, [_i, _vp, _vp, _vp]),
     "rod_l2_flush": (_i, [_vp, _sz, _vp]),
+    "rod_dl_layered": (_i, [_LP, _vp, _i, _i, _i, _YP, _vp]),
     "rod_dl_arm_match_encode": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_dl_odm_target": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_dl_decode": (_i, [_LP, _vp, _vp, _vp, _i, _vp, _vp]),
@@ -118,6 +119,91 @@ def require_cuda(t, name):
 
 def stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class device_guard:
+    """`torch.cuda.device(dev)` only when `dev` is not already current (the common case is free)."""
+    __slots__ = ("_ctx",)
+
+    def __init__(self, device):
+        self._ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+
+class LayerList(list):
+    """The reference's "list over layers" backed by ONE flat [B, N(, inner)] tensor.
+
+    Behaves like the plain Python list of per-layer tensors the reference returns (the views are
+    created when first touched), and remembers the flat tensor so that our own functions can
+    hand it on without re-deriving six pointers (`refine_groundtruth` -> `det_groundtruth`)."""
+
+    def __init__(self, flat, table, batched, trailing_one):
+        super().__init__()
+        self.flat, self.table, self.batched, self.trailing_one = flat, table, batched, trailing_one
+        self._ready = False
+
+    def _fill(self):
+        if not self._ready:
+            self._ready = True
+            super().extend(self.table.split(self.flat, self.batched, self.trailing_one))
+
+    def __len__(self):
+        return self.table.n_layers
+
+    def __getitem__(self, i):
+        self._fill()
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __repr__(self):
+        self._fill()
+        return super().__repr__()
+
+    def __eq__(self, other):
+        self._fill()
+        return super().__eq__(other)
+
+    __hash__ = None
+
+
+_DT = {torch.float32: (2, 32), torch.int32: (0, 32), torch.int64: (0, 64)}
+
+
+def layered_arg(ts, table, inner, dtype, args, batch_box):
+    """rod_layered_t for a per-layer list.  Our own LayerList (same table) is described from its
+    flat tensor directly; anything else goes through DLPack and is validated in C."""
+    out = Layered()
+    if isinstance(ts, LayerList) and ts.table is table and ts.flat.dtype == dtype and ts.batched:
+        flat = ts.flat
+        esz = flat.element_size()
+        base, stride = flat.data_ptr(), flat.stride(0)
+        for l in range(table.n_layers):
+            out.base[l] = base + table.offsets[l] * inner * esz
+            out.batch_stride[l] = stride
+        if batch_box[0] < 0:
+            batch_box[0] = flat.shape[0]
+        elif batch_box[0] != flat.shape[0]:
+            raise ValueError("per-layer lists disagree on the batch size")
+        args._keep.append(flat)
+        return out
+    if len(ts) != table.n_layers:
+        raise ValueError("list has %d layers, anchors have %d" % (len(ts), table.n_layers))
+    code, bits = _DT[dtype]
+    b = ctypes.c_int(batch_box[0])
+    check(lib.rod_dl_layered(table.layout, args.many(list(ts)), inner, code, bits, ctypes.byref(out), ctypes.byref(b)))
+    batch_box[0] = b.value
+    return out
 
 
 def float_array(vals):

@@ -85,6 +85,14 @@ static int dl_layered(const DLTensor* const* ts, const rod_layout_t* L, int inne
 
 using namespace rod;
 
+extern "C" int rod_dl_layered(const rod_layout_t* layout, const DLTensor* const* tensors, int inner, int dtype_code,
+                              int dtype_bits, rod_layered_t* out, int* batch) {
+  int rc = check_layout(layout);
+  if (rc) return rc;
+  ROD_REQUIRE(out != nullptr && batch != nullptr && inner >= 1, "rod_dl_layered: bad arguments");
+  return dl_layered(tensors, layout, inner, dtype_code, dtype_bits, batch, "tensors", out);
+}
+
 extern "C" int rod_dl_arm_match_encode(const rod_layout_t* layout, const DLTensor* anchors_corner,
                                        const DLTensor* anchors_center, const float* thresholds,
                                        const DLTensor* center_bboxes, const DLTensor* labels,

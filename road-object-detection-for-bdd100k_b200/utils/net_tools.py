@@ -101,11 +101,17 @@ def _check_list(ts, table, name):
     return list(ts)
 
 
+_THR_CACHE = {}
+
+
 def _thresholds(vals, table, name):
-    vals = list(vals)
-    if len(vals) < table.n_layers:
-        raise ValueError("%s has %d entries for %d layers" % (name, len(vals), table.n_layers))
-    return _abi.float_array(vals[:table.n_layers])
+    key = (tuple(vals), table.n_layers)
+    arr = _THR_CACHE.get(key)
+    if arr is None:
+        if len(key[0]) < table.n_layers:
+            raise ValueError("%s has %d entries for %d layers" % (name, len(key[0]), table.n_layers))
+        arr = _THR_CACHE[key] = _abi.float_array(key[0][:table.n_layers])
+    return arr
 
 
 # --------------------------------------------------------------------------------- encode / decode / jaccard
@@ -142,7 +148,7 @@ def _decode(table, refine_out, det_out, to_corner):
     if B == 0:
         return out
     a = _abi.DLArgs()
-    with torch.cuda.device(dev):
+    with _abi.device_guard(dev):
         _abi.check(_abi.lib.rod_dl_decode(table.layout, a.one(table.center), a.many(refine_out),
                                           a.many(det_out), 1 if to_corner else 0, a.one(out),
                                           _abi.stream_ptr(dev)))
@@ -206,15 +212,16 @@ def refine_groundtruth(anchors_all_layer, center_bboxes, labels, method, scope="
     pos = torch.empty((B, N), dtype=torch.int32, device=dev)
     idx = torch.empty((B, N), dtype=torch.int32, device=dev) if return_match_index else None
     a = _abi.DLArgs()
-    with torch.cuda.device(dev):
+    with _abi.device_guard(dev):
         _abi.check(_abi.lib.rod_dl_arm_match_encode(
             table.layout, a.one(table.corner), a.one(table.center), thr, a.one(cb), a.one(lab),
             a.one(gt_counts), int(method.value), a.one(gt), a.one(cbo), a.one(lbo), a.one(pos), a.one(idx),
             _abi.stream_ptr(dev)))
-    res = (table.split(gt, batched), table.split(cbo, batched), table.split(lbo, batched, True),
-           table.split(pos, batched, True))
+    LL = _abi.LayerList
+    res = (LL(gt, table, batched, False), LL(cbo, table, batched, False), LL(lbo, table, batched, True),
+           LL(pos, table, batched, True))
     if return_match_index:
-        return res + (table.split(idx, batched),)
+        return res + (LL(idx, table, batched, False),)
     return res
 
 
@@ -224,28 +231,37 @@ def det_groundtruth(refine_out, offset_gt, cbboxes, refine_labels, refine_pos_ma
     """ODM target generation (utils/net_tools.py:431-475): four lists over layers of
     det_gt[B,fh,fw,A,4], mask[B,fh,fw,A,1] (int32), det_labels[B,fh,fw,A,1] (int32),
     iou[B,fh,fw,A]."""
-    dev = _f32(refine_out[0], "refine_out").device
+    first = refine_out.flat if isinstance(refine_out, _abi.LayerList) else refine_out[0]
+    dev = _abi.require_cuda(first, "refine_out").device
     table = table_for(anchors, dev)
-    ro = [_f32(t, "refine_out") for t in _check_list(refine_out, table, "refine_out")]
-    og = [_f32(t, "offset_gt") for t in _check_list(offset_gt, table, "offset_gt")]
-    cb = [_f32(t, "cbboxes") for t in _check_list(cbboxes, table, "cbboxes")]
-    lb = [t.to(torch.int32) for t in _check_list(refine_labels, table, "refine_labels")]
-    pm = [t.to(torch.int32) for t in _check_list(refine_pos_mask, table, "refine_pos_mask")]
     thr = _thresholds(config.det_pos_jac_val_all_layers if thresholds is None else thresholds,
                       table, "det_pos_jac_val_all_layers")
-    B, N = ro[0].shape[0], table.n
-    det_gt = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
-    mask = torch.empty((B, N), dtype=torch.int32, device=dev)
-    dlab = torch.empty((B, N), dtype=torch.int32, device=dev)
-    iou = torch.empty((B, N), dtype=torch.float32, device=dev)
-    if B:
-        a = _abi.DLArgs()
-        with torch.cuda.device(dev):
-            _abi.check(_abi.lib.rod_dl_odm_target(
-                table.layout, a.one(table.center), thr, a.many(ro), a.many(og), a.many(cb), a.many(lb),
-                a.many(pm), a.one(det_gt), a.one(mask), a.one(dlab), a.one(iou), _abi.stream_ptr(dev)))
-    return (table.split(det_gt), table.split(mask, True, True), table.split(dlab, True, True),
-            table.split(iou))
+    a = _abi.DLArgs()
+    bb = [-1]
+    f32, i32 = torch.float32, torch.int32
+
+    def ints(ts):      # the reference casts labels / masks to int32 (utils/net_tools.py:469)
+        if isinstance(ts, _abi.LayerList) or all(t.dtype == i32 for t in ts):
+            return ts
+        return [t.to(i32) for t in ts]
+    with _abi.device_guard(dev):
+        ro = _abi.layered_arg(refine_out, table, 4, f32, a, bb)
+        og = _abi.layered_arg(offset_gt, table, 4, f32, a, bb)
+        cb = _abi.layered_arg(cbboxes, table, 4, f32, a, bb)
+        lb = _abi.layered_arg(ints(refine_labels), table, 1, i32, a, bb)
+        pm = _abi.layered_arg(ints(refine_pos_mask), table, 1, i32, a, bb)
+        B, N = bb[0], table.n
+        det_gt = torch.empty((B, N, 4), dtype=f32, device=dev)
+        mask = torch.empty((B, N), dtype=i32, device=dev)
+        dlab = torch.empty((B, N), dtype=i32, device=dev)
+        iou = torch.empty((B, N), dtype=f32, device=dev)
+        if B:
+            _abi.check(_abi.lib.rod_odm_target(
+                table.layout, table.center.data_ptr(), thr, ro, og, cb, lb, pm, B, det_gt.data_ptr(),
+                mask.data_ptr(), dlab.data_ptr(), iou.data_ptr(), _abi.stream_ptr(dev)))
+    LL = _abi.LayerList
+    return (LL(det_gt, table, True, False), LL(mask, table, True, True), LL(dlab, table, True, True),
+            LL(iou, table, True, False))
 
 
 # --------------------------------------------------------------------------------- a11 select
@@ -336,7 +352,7 @@ def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_thr
         if clipping_bbox is not None:
             clip = torch.as_tensor(clipping_bbox, dtype=torch.float32, device=dev).reshape(4).contiguous()
         a = _abi.DLArgs()
-        with torch.cuda.device(dev):
+        with _abi.device_guard(dev):
             _abi.check(_abi.lib.rod_dl_detect(
                 lay, a.one(center), a.many(preds), a.many(locs), a.many(refine_out), a.many(det_out), 0, thr,
                 float(nms_threshold), int(top_k), int(keep_top_k), a.one(clip), a.one(scores), a.one(boxes),
