@@ -422,7 +422,7 @@ def main():
         for name, stress in (("decode_nms", False), ("nms_stress", True)):
             line[name] = bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_loop, hbm_gbs, N)
 
-    if rank == 0 and not args.skip_cpu:
+    if rank == 0 and not args.skip_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline("match_encode", args.cpu_seconds)
         if not args.skip_secondary:
             line["decode_nms"]["cpu_baseline"] = cpu_baseline("decode_nms", args.cpu_seconds)
@@ -462,6 +462,8 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
                 s["gout"] = run(s)
             s["graph"] = g
 
+    pending = [None]
+
     def step(i):
         s = sets[i % n_sets]
         if use_graphs:
@@ -469,8 +471,10 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
             cnt = s["gout"][2]
         else:
             cnt = run(s)[2]
-        if world > 1:                            # NCCL all-gather of per-rank detection counts
-            allgather_counts(cnt, B * world)
+        if world > 1:                            # NCCL all-gather of per-rank detection counts, one step behind
+            if pending[0] is not None:
+                pending[0].result()
+            pending[0] = allgather_counts(cnt, B * world, async_op=True)
 
     steps = max(10, args.steps // 4)
     ms = time_loop(step, steps, max(3, args.warmup // 4))

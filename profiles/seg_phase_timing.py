@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Per-phase clock64() breakdown of segment_kernel (debug hook rod_debug_set_timing)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from rodet_b200 import _abi  # noqa: E402
+from rodet_b200.anchor_table import AnchorTable  # noqa: E402
+from rodet_b200.utils import net_tools  # noqa: E402
+
+stress = len(sys.argv) > 1 and sys.argv[1] == "stress"
+dev = torch.device("cuda:0")
+table = AnchorTable.from_anchors(bench.make_anchors(), dev)
+B = 64
+p, ro, do = bench.host_inputs_detect(0, B, stress)
+tl = lambda a, t: [torch.from_numpy(x).to(dev) for x in bench.split_np(a, bench.SHAPES, t)]
+P, RO, DO = tl(p, (11,)), tl(ro, (4,)), tl(do, (4,))
+dbg = torch.zeros((2 * 11 * B, 8), dtype=torch.int64, device=dev)
+_abi.lib.rod_debug_set_timing.argtypes = [ctypes.c_void_p]
+run = lambda: net_tools.decode_detected_bboxes(table, RO, DO, P, select_threshold=0.3, nms_threshold=0.45, top_k=400, keep_top_k=200)
+for _ in range(3):
+    run()
+_abi.lib.rod_debug_set_timing(dbg.data_ptr())
+run()
+torch.cuda.synchronize()
+_abi.lib.rod_debug_set_timing(None)
+allrows = dbg.cpu().numpy()
+d = allrows[B:11 * B]                          # class 0 rows are skipped
+
+t = d[:, :6].astype(np.float64)
+names = ["load+filter", "sort", "gather/decode", "nms", "emit"]
+dur = np.diff(t, axis=1)
+print("segments", len(d), "mean kept", d[:, 6].mean(), "mean list", d[:, 7].mean())
+for n, v in zip(names, dur.mean(0)):
+    print("%-14s %8.0f cycles  %6.2f us @1.9GHz" % (n, v, v / 1900.0))
+print("total          %8.0f cycles  %6.2f us ; start spread %.1f us, end spread %.1f us" % (
+    (t[:, 5] - t[:, 0]).mean(), (t[:, 5] - t[:, 0]).mean() / 1900.0,
+    (t[:, 0].max() - t[:, 0].min()) / 1900.0, (t[:, 5].max() - t[:, 5].min()) / 1900.0))

@@ -420,13 +420,14 @@ struct SegParams {
   const unsigned* hist;
   const unsigned* flag;
   const unsigned* cnt2;
+  long long* dbg;            // optional per-segment phase timestamps (rod_debug_set_timing), else NULL
   unsigned* over;            // out: 1 when the segment must be redone by the exact general kernels
   int chunks, spc, force_dense;
 };
 
 // bytes of the aliased region: sort keys, later {kept boxes, overlap words, batch rows, kept areas}
 __host__ __device__ inline size_t seg_region_a(int cap, int keep) {
-  const size_t a = (size_t)cap * 16 + 1024 * 4, b = (size_t)keep * (16 + 8 + 4) + 128 * 8;
+  const size_t a = (size_t)cap * 16 + 1024 * 4, b = (size_t)keep * (16 + 4) + 64 * 8 * 4;
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
@@ -455,11 +456,9 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   const int cap = P.cap, k = P.k, keep = P.keep;
   const size_t regionA = seg_region_a(cap, keep);
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_raw);
-  float4* s_kbox = reinterpret_cast<float4*>(s_raw);                                   // [keep]
-  unsigned long long* s_ov = reinterpret_cast<unsigned long long*>(s_kbox + keep);     // [keep]
-  unsigned long long* s_bm = s_ov + keep;                                              // [64] batch rows: overlap words
-  unsigned long long* s_cm = s_bm + 64;                                                // [64] batch columns: suppressors
-  float* s_karea = reinterpret_cast<float*>(s_cm + 64);                                // [keep]
+  float4* s_kbox = reinterpret_cast<float4*>(s_raw);                                   // [keep] kept boxes
+  unsigned* s_cmw = reinterpret_cast<unsigned*>(s_kbox + keep);                        // [64][kSegWarps] partial column masks
+  float* s_karea = reinterpret_cast<float*>(s_cmw + 64 * kSegWarps);                   // [keep] kept areas
   float4* s_box = reinterpret_cast<float4*>(s_raw + regionA);
   float4* s_nbox = s_box + k;
   float* s_area = reinterpret_cast<float*>(s_nbox + k);
@@ -472,6 +471,8 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   const int c = (int)(r / P.batch), b = (int)(r % P.batch);
   if (c == P.ignore_class) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#define SEG_T(i) do { if (P.dbg != nullptr && tid == 0) P.dbg[r * 8 + (i)] = clock64(); } while (0)
+  SEG_T(0);
   // ---- 0. candidates at or above the threshold bin -> s_keys[0, cnt)
   __shared__ int s_n, s_tbv;
   __shared__ unsigned s_part[kMaxChunks];
@@ -521,6 +522,7 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     }
   }
 
+  SEG_T(1);
   // ---- 1. sort the candidate list: descending (score bits, ~anchor) = tf.nn.top_k order.
   // Counting sort on the 1024 score bins the histogram pass already uses (monotone in the score),
   // then an exact rank inside each bin (bins hold a handful of entries; all-tied inputs stay
@@ -586,6 +588,7 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     }
     __syncthreads();
   }
+  SEG_T(2);
   const int m = min(cnt, k);                          // real candidates entering NMS
 
   // ---- 2. gather / decode the m boxes (evaluate.py:141-142), select-stage mask is 1 for all of them
@@ -613,95 +616,109 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   }
   __syncthreads();                                    // keys are dead from here: region A becomes the mask
 
+  SEG_T(3);
   // ---- 3. greedy NMS in batches of 64 candidates against the kept list.
   // A candidate is kept iff no earlier KEPT box has IoU > thr with it (tf.image.non_max_suppression).
-  // Per batch: (a) ballot the exact "positive intersection" predicate of the 64 candidates (two
-  // per lane, in registers) against every kept box (broadcast from shared memory) and against the
-  // batch itself; (b) run the IoU test only on intersecting pairs; (c) one warp resolves the
-  // 64 x 64 intra-batch dependencies serially; (d) survivors join the kept list.
+  // Every lane owns two candidates of the batch (boxes + areas in registers).  Phase 1 (all warps):
+  // the lane tests its candidates against the kept boxes of its warp's share (rows broadcast from
+  // shared memory; exact 4-compare intersection predicate, IoU only when it holds) and against the
+  // batch rows of its warp, accumulating "dead" bits and per-column suppressor masks in registers.
+  // Phase 2 (warp 0): resolve the 64 x 64 intra-batch dependencies and append the survivors.
   const float thr = P.nms_thr;
   const float4 none = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+  auto suppresses = [&](const float4& r, float ar, const float4& c, float ac) -> bool {
+    const float ih = __fsub_rn(fminf(r.z, c.z), fmaxf(r.x, c.x));
+    const float iw = __fsub_rn(fminf(r.w, c.w), fmaxf(r.y, c.y));
+    const float inter = __fmul_rn(ih, iw);
+    const float den = __fsub_rn(__fadd_rn(ar, ac), inter);
+    return (thr >= 0.f && den > 1e-30f) ? iou_exceeds(inter, den, thr) : (__fdiv_rn(inter, den) > thr);
+  };
   int nk = 0;
   for (int p0 = 0; p0 < m && nk < keep; p0 += 64) {
     const int nb = min(64, m - p0);
     const int c0 = p0 + lane, c1 = c0 + 32;
     const float4 b0 = c0 < m ? s_nbox[c0] : none;
     const float4 b1 = c1 < m ? s_nbox[c1] : none;
-    // (a) overlap words: kept rows j = warp, warp+8, ... ; batch rows r = warp*8 .. warp*8+7
-#pragma unroll 4
-    for (int j = warp; j < nk; j += kSegWarps) {
-      const float4 kb = s_kbox[j];
-      const bool q0 = (kb.z > b0.x) && (b0.z > kb.x) && (kb.w > b0.y) && (b0.w > kb.y);
-      const bool q1 = (kb.z > b1.x) && (b1.z > kb.x) && (kb.w > b1.y) && (b1.w > kb.y);
-      const unsigned lo = __ballot_sync(0xffffffffu, q0), hi = __ballot_sync(0xffffffffu, q1);
-      if (lane == 0) s_ov[j] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-    }
-#pragma unroll
-    for (int rr = 0; rr < 64 / kSegWarps; ++rr) {
-      const int rrow = warp * (64 / kSegWarps) + rr;
-      if (rrow < nb) {
-        const float4 bi = s_nbox[p0 + rrow];
-        const bool q0 = (bi.z > b0.x) && (b0.z > bi.x) && (bi.w > b0.y) && (b0.w > bi.y);
-        const bool q1 = (bi.z > b1.x) && (b1.z > bi.x) && (bi.w > b1.y) && (b1.w > bi.y);
-        const unsigned lo = __ballot_sync(0xffffffffu, q0), hi = __ballot_sync(0xffffffffu, q1);
-        unsigned long long word = (unsigned long long)lo | ((unsigned long long)hi << 32);
-        word &= (rrow == 63) ? 0ull : ~((2ull << rrow) - 1ull);       // columns after the row only
-        if (lane == 0) s_bm[rrow] = word;
-      }
-    }
+    const float a0 = c0 < m ? s_area[c0] : 0.f, a1 = c1 < m ? s_area[c1] : 0.f;
     if (tid == 0) s_dead = 0ull;
-    if (tid < 64) s_cm[tid] = 0ull;
-    __syncthreads();
-    // (b) exact IoU > thr on the intersecting pairs; two threads per 64-bit word (32 columns each)
-    for (int t = tid; t < 2 * (nk + nb); t += kSegBlock) {
-      const int wd = t >> 1, half = t & 1;
-      const bool vs_kept = wd < nk;
-      unsigned maybe = (unsigned)((vs_kept ? s_ov[wd] : s_bm[wd - nk]) >> (half << 5));
-      if (maybe) {
-        const float4 bi = vs_kept ? s_kbox[wd] : s_nbox[p0 + wd - nk];
-        const float ai = vs_kept ? s_karea[wd] : s_area[p0 + wd - nk];
-        unsigned long long bits = 0ull;
-        while (maybe) {
-          const int q = (__ffs(maybe) - 1) + (half << 5);
-          maybe &= maybe - 1;
-          const float4 bj = s_nbox[p0 + q];
-          const float ih = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
-          const float iw = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
-          const float inter = __fmul_rn(ih, iw);
-          const float den = __fsub_rn(__fadd_rn(ai, s_area[p0 + q]), inter);
-          const bool sup = (thr >= 0.f && den > 1e-30f) ? iou_exceeds(inter, den, thr) : (__fdiv_rn(inter, den) > thr);
-          bits |= (unsigned long long)sup << q;
-        }
-        if (vs_kept) {
-          if (bits) atomicOr(&s_dead, bits);
-        } else {
-          // column view of the intra-batch suppression relation: s_cm[q] = rows that suppress q
-          const unsigned long long me = 1ull << (wd - nk);
-          while (bits) {
-            const int q = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            atomicOr(&s_cm[q], me);
-          }
-        }
+    // -- vs the kept list: warp w takes rows w, w+8, ...  First a branch-free pass that only records
+    // which rows intersect the lane's candidates (pipelined broadcast loads + compares), then the
+    // IoU test for the recorded rows only (a few per lane).
+    bool d0 = false, d1 = false;
+    for (int jb = warp; jb < nk; jb += 32 * kSegWarps) {
+      unsigned h0 = 0u, h1 = 0u;
+      const int ni = min(32, (nk - jb + kSegWarps - 1) / kSegWarps);      // rows of this pass (warp-uniform)
+#pragma unroll 4
+      for (int i = 0; i < ni; ++i) {
+        const float4 kb = s_kbox[jb + i * kSegWarps];
+        h0 |= (unsigned)((kb.z > b0.x) && (b0.z > kb.x) && (kb.w > b0.y) && (b0.w > kb.y)) << i;
+        h1 |= (unsigned)((kb.z > b1.x) && (b1.z > kb.x) && (kb.w > b1.y) && (b1.w > kb.y)) << i;
+      }
+      while (h0 && !d0) {
+        const int j = jb + (__ffs(h0) - 1) * kSegWarps;
+        h0 &= h0 - 1;
+        d0 = suppresses(s_kbox[j], s_karea[j], b0, a0);
+      }
+      while (h1 && !d1) {
+        const int j = jb + (__ffs(h1) - 1) * kSegWarps;
+        h1 &= h1 - 1;
+        d1 = suppresses(s_kbox[j], s_karea[j], b1, a1);
       }
     }
+    // -- vs the batch itself: warp w takes rows 8w .. 8w+7; bit i of cm = row 8w+i suppresses my column
+    unsigned cm0 = 0u, cm1 = 0u;
+    {
+      unsigned h0 = 0u, h1 = 0u;
+      const int r0 = warp * (64 / kSegWarps);
+#pragma unroll
+      for (int rr = 0; rr < 64 / kSegWarps; ++rr) {
+        const int rrow = r0 + rr;                       // warp-uniform
+        if (rrow < nb) {
+          const float4 bi = s_nbox[p0 + rrow];
+          h0 |= (unsigned)(lane > rrow && (bi.z > b0.x) && (b0.z > bi.x) && (bi.w > b0.y) && (b0.w > bi.y)) << rr;
+          h1 |= (unsigned)(lane + 32 > rrow && (bi.z > b1.x) && (b1.z > bi.x) && (bi.w > b1.y) && (b1.w > bi.y)) << rr;
+        }
+      }
+      while (h0) {
+        const int rr = __ffs(h0) - 1;
+        h0 &= h0 - 1;
+        cm0 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], b0, a0) << rr;
+      }
+      while (h1) {
+        const int rr = __ffs(h1) - 1;
+        h1 &= h1 - 1;
+        cm1 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], b1, a1) << rr;
+      }
+    }
+    s_cmw[lane * kSegWarps + warp] = cm0;
+    s_cmw[(lane + 32) * kSegWarps + warp] = cm1;
+    __syncthreads();                                   // s_dead reset + partial masks visible
+    {
+      const unsigned long long dw = (unsigned long long)__ballot_sync(0xffffffffu, d0) |
+                                    ((unsigned long long)__ballot_sync(0xffffffffu, d1) << 32);
+      if (lane == 0 && dw) atomicOr(&s_dead, dw);
+    }
     __syncthreads();
-    // (c) resolve the intra-batch dependencies (warp 0): candidate q is dead if a KEPT earlier
-    // candidate suppresses it, kept once no undecided earlier candidate could.  Each round decides
-    // at least the lowest undecided candidate; chains are short, so a few rounds suffice.
+    // -- resolve (warp 0): candidate q is dead if a KEPT earlier candidate suppresses it, kept once no
+    // undecided earlier candidate could; every round decides at least the lowest undecided one.
     if (warp == 0) {
+      unsigned long long cmA = 0ull, cmB = 0ull;       // suppressor rows of my two candidates
+#pragma unroll
+      for (int w = 0; w < kSegWarps; ++w) {
+        cmA |= (unsigned long long)s_cmw[lane * kSegWarps + w] << (w * (64 / kSegWarps));
+        cmB |= (unsigned long long)s_cmw[(lane + 32) * kSegWarps + w] << (w * (64 / kSegWarps));
+      }
       unsigned long long U = ~s_dead;
       if (nb < 64) U &= (1ull << nb) - 1ull;
       unsigned long long K = 0ull;
-      const unsigned long long cm0 = s_cm[lane], cm1 = s_cm[lane + 32];
       while (U) {
         const bool u0 = (U >> lane) & 1ull, u1 = (U >> (lane + 32)) & 1ull;
-        const bool d0 = u0 && (cm0 & K), d1 = u1 && (cm1 & K);
-        const bool k0 = u0 && !d0 && !(cm0 & U), k1 = u1 && !d1 && !(cm1 & U);
+        const bool x0 = u0 && (cmA & K), x1 = u1 && (cmB & K);
+        const bool k0 = u0 && !x0 && !(cmA & U), k1 = u1 && !x1 && !(cmB & U);
         const unsigned long long newK = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
                                         ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
-        const unsigned long long newD = (unsigned long long)__ballot_sync(0xffffffffu, d0) |
-                                        ((unsigned long long)__ballot_sync(0xffffffffu, d1) << 32);
+        const unsigned long long newD = (unsigned long long)__ballot_sync(0xffffffffu, x0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, x1) << 32);
         K |= newK;
         U &= ~(newK | newD);
       }
@@ -712,23 +729,25 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
         const int pos = room <= cl ? (int)__fns(lo32, 0u, room) : 32 + (int)__fns(hi32, 0u, room - cl);
         K &= (pos >= 63) ? ~0ull : ((2ull << pos) - 1ull);
       }
+      // append the survivors to the kept list, in order (lane owns candidates lane and lane + 32)
+      if ((K >> lane) & 1ull) {
+        const int pos = nk + __popcll(K & ((1ull << lane) - 1ull));
+        s_selected[pos] = c0; s_kbox[pos] = b0; s_karea[pos] = a0;
+      }
+      if ((K >> (lane + 32)) & 1ull) {
+        const int pos = nk + __popcll(K & ((1ull << (lane + 32)) - 1ull));
+        s_selected[pos] = c1; s_kbox[pos] = b1; s_karea[pos] = a1;
+      }
       if (lane == 0) s_sel = K;
     }
     __syncthreads();
-    // (d) append the survivors to the kept list, in order
-    const unsigned long long sel = s_sel;
-    if (tid < 64 && ((sel >> tid) & 1ull)) {
-      const int pos = nk + __popcll(sel & ((1ull << tid) - 1ull));
-      s_selected[pos] = p0 + tid;
-      s_kbox[pos] = s_nbox[p0 + tid];
-      s_karea[pos] = s_area[p0 + tid];
-    }
-    nk += __popcll(sel);
-    __syncthreads();
+    nk += __popcll(s_sel);
   }
+
   if (tid == 0) s_nsel = nk;
   __syncthreads();
 
+  SEG_T(4);
   // ---- 5. emit keep rows: survivors in order, then pad_axis zeros (clip applies to all rows)
   const int nsel = s_nsel;
   float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -754,7 +773,12 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     nonzero = __reduce_add_sync(0xffffffffu, nonzero);
     if (lane == 0 && nonzero) atomicAdd(out_counts + r, nonzero);
   }
+  SEG_T(5);
+  if (P.dbg != nullptr && tid == 0) { P.dbg[r * 8 + 6] = nk; P.dbg[r * 8 + 7] = cnt; }
+#undef SEG_T
 }
+
+static long long* g_seg_dbg = nullptr;
 
 static size_t seg_smem_bytes(int cap, int k, int keep) {
   return seg_region_a(cap, keep) + (size_t)k * (16 + 16 + 4 + 4) + (size_t)keep * 4 + 16;
@@ -857,7 +881,7 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   G.center = anchors_center;
   G.L = L; G.batch = batch; G.ignore_class = ignore_class; G.cap = cap; G.k = top_k; G.keep = keep;
   G.nms_thr = nms_thr; G.clip = clip;
-  G.cnt2 = g_cnt2; G.over = g_over;
+  G.cnt2 = g_cnt2; G.over = g_over; G.dbg = g_seg_dbg;
   G.list1 = g_list; G.cnt1 = g_cnt1; G.hist = g_hist; G.flag = g_flag;
   G.chunks = n_chunks; G.spc = spc; G.force_dense = force_dense;
   const size_t smem = seg_smem_bytes(cap, top_k, keep);
@@ -871,3 +895,7 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
 }
 
 }  // namespace rod
+
+// Debug hook (not part of the public header): per-segment clock64() stamps of the segment kernel's
+// phases, 8 x int64 per (class, image) row.  Pass NULL to switch it off.
+extern "C" void rod_debug_set_timing(long long* device_buf) { rod::g_seg_dbg = device_buf; }

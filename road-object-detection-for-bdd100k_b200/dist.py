@@ -20,18 +20,44 @@ def shard_range(n_images: int, rank: int, world: int):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def allgather_counts(counts: torch.Tensor, n_images: int, group=None) -> torch.Tensor:
+class PendingCounts:
+    """Handle of an in-flight count all-gather; `result()` waits and returns the `[C, n_images]` tensor."""
+
+    def __init__(self, work, parts, sizes, even):
+        self._work, self._parts, self._sizes, self._even = work, parts, sizes, even
+
+    def result(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        if self._even:                                   # parts: [world, C, B_local]
+            w, c, bl = self._parts.shape
+            return self._parts.permute(1, 0, 2).reshape(c, w * bl)
+        return torch.cat([p[:, :e - b] for p, (b, e) in zip(self._parts, self._sizes)], dim=1)
+
+
+def allgather_counts(counts: torch.Tensor, n_images: int, group=None, async_op: bool = False):
     """counts: this rank's `[C, B_local]` int32 detection counts (B_local = its shard_range size).
-    Returns the global `[C, n_images]` tensor on every rank.  Uneven shards are padded to the
-    largest shard for the collective and trimmed afterwards."""
+    Returns the global `[C, n_images]` tensor on every rank (or, with `async_op=True`, a
+    `PendingCounts` whose `result()` yields it, so the collective runs on NCCL's stream while the
+    next batch is processed).  Even shards use one `all_gather_into_tensor`; uneven shards are
+    padded to the largest shard and trimmed afterwards."""
     if not dist.is_available() or not dist.is_initialized():
-        return counts
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+        return PendingCounts(None, counts.unsqueeze(0), None, True) if async_op else counts
+    world = dist.get_world_size(group)
     sizes = [shard_range(n_images, r, world) for r in range(world)]
     width = max(e - b for b, e in sizes)
     c = counts.shape[0]
-    mine = counts.new_zeros((c, width))
-    mine[:, :counts.shape[1]] = counts
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine.contiguous(), group=group)
-    return torch.cat([p[:, :e - b] for p, (b, e) in zip(parts, sizes)], dim=1)
+    even = (all(e - b == width for b, e in sizes) and counts.shape[1] == width
+            and dist.get_backend(group) == "nccl")       # gloo: list form only
+    if even:
+        out = counts.new_empty((world, c, width))
+        work = dist.all_gather_into_tensor(out, counts.contiguous(), group=group, async_op=True)
+        pending = PendingCounts(work, out, sizes, True)
+    else:
+        mine = counts.new_zeros((c, width))
+        mine[:, :counts.shape[1]] = counts
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        work = dist.all_gather(parts, mine, group=group, async_op=True)
+        pending = PendingCounts(work, parts, sizes, False)
+    return pending if async_op else pending.result()
