@@ -52,6 +52,8 @@ def parse_args():
     p.add_argument("--batch", type=int, default=32, help="images per GPU per step, match_encode")
     p.add_argument("--batch-detect", type=int, default=64, help="images per GPU per step, decode_nms")
     p.add_argument("--no-graphs", action="store_true", help="launch through Python every step instead of CUDA graphs")
+    p.add_argument("--streams", type=int, default=4,
+                   help="CUDA streams that consecutive (independent) batches alternate on; 1 = strictly serial steps")
     p.add_argument("--skip-secondary", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -82,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -273,14 +275,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def time_loop(step_fn, steps, warmup):
-        for i in range(warmup):
-            step_fn(i)
+    side_streams = [torch.cuda.Stream(dev) for _ in range(max(1, args.streams))]
+
+    def time_loop(step_fn, steps, warmup, n_streams=1):
+        """K steps between two CUDA events on the launching stream.  With n_streams > 1 consecutive
+        steps (independent batches, disjoint buffers) alternate over that many streams, all forked
+        from / joined to the timing stream, so a batch's memory-bound kernels overlap the next
+        batch's issue-bound ones."""
+        lanes = side_streams[:n_streams] if n_streams > 1 else [stream]
+
+        def run(first, count):
+            if n_streams > 1:
+                fork = torch.cuda.Event()
+                fork.record(stream)
+                for s in lanes:
+                    s.wait_event(fork)
+            for i in range(count):
+                with torch.cuda.stream(lanes[i % len(lanes)]):
+                    step_fn(first + i)
+            if n_streams > 1:
+                for s in lanes:
+                    j = torch.cuda.Event()
+                    j.record(s)
+                    stream.wait_event(j)
+        run(0, warmup)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(steps):
-            step_fn(warmup + i)
+        run(warmup + (warmup % 2), steps)
         e1.record(stream)
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
@@ -292,7 +314,7 @@ def main():
     B = args.batch
     # several independent input/output sets, rotated every step, so the working set of
     # consecutive steps (~150 MB each: 66 MB read + 80 MB written) exceeds the 126 MB L2
-    n_sets = 4
+    n_sets = max(4, 2 * args.streams)
     sets = []
     for s in range(n_sets):
         c, l, k, ro = host_inputs_match((rank * n_sets + s) * B, B)
@@ -336,14 +358,15 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = time_loop(step_m, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_total = time_loop(step_m, args.steps, args.warmup, args.streams if use_graphs else 1)
     ms_step = ms_total / args.steps
+    ms_step_serial = time_loop(step_m, args.steps, args.warmup, 1) / args.steps if args.streams > 1 else ms_step
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # per-kernel launch times for the roofline (same stream, CUDA events, rotating sets)
     ms_arm = time_loop(step_arm, args.steps, max(3, args.warmup // 4)) / args.steps
     ms_odm = time_loop(step_odm, args.steps, max(3, args.warmup // 4)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None      # sampled across the timed region and the per-kernel loops
     mean_g = float(np.mean([s["host"][2].mean() for s in sets]))
     bytes_arm = B * (40 * N + 20 * mean_g)                     # write 40 N, read 20 G
     bytes_odm = B * 84 * N                                     # read 56 N + write 28 N
@@ -412,7 +435,8 @@ def main():
                                "BASELINE configs[1]", "batch_per_gpu": B, "global_batch": B * world,
                    "image": "512x512", "anchors": N, "max_gt": 100, "mean_gt": mean_g,
                    "l2": "inputs larger than L2: %d rotating input/output sets (~150 MB each)" % n_sets,
-                   "launch": "CUDA graph replay" if use_graphs else "python launches",
+                   "launch": ("CUDA graph replay; consecutive batches alternate over %d streams" % args.streams)
+                   if use_graphs else "python launches", "ms_per_step_1stream": ms_step_serial,
                    "parallelism": "image-sharded, no collective"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
     }
@@ -438,7 +462,7 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
     from rodet_b200.dist import allgather_counts
     from rodet_b200.utils import net_tools
     B = args.batch_detect
-    n_sets = 2                                      # 2 x 180 MB of inputs > 126 MB L2
+    n_sets = max(2, args.streams)                   # >= 2 x 180 MB of inputs > 126 MB L2; one set per stream
     sets = []
     for s in range(n_sets):
         p, ro, do = host_inputs_detect(500_000 + (rank * n_sets + s) * B, B, stress)
@@ -477,10 +501,13 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
             pending[0] = allgather_counts(cnt, B * world, async_op=True)
 
     steps = max(10, args.steps // 4)
-    ms = time_loop(step, steps, max(3, args.warmup // 4))
+    ns = args.streams if use_graphs else 1
+    ms = time_loop(step, steps, max(4, args.warmup // 4), ns)
+    ms_serial = time_loop(step, steps, max(4, args.warmup // 4), 1) if ns > 1 else ms
     value = world * B * steps / (ms * 1e-3)
     alg_bytes = B * (76 * N + (N_CLASSES - 1) * KEEP * 20)
     res = {"metric": "images/sec (decode+NMS)", "value": value, "unit": "images/s", "ms_per_step": ms / steps,
+           "ms_per_step_1stream": ms_serial / steps, "streams": ns,
            "steps": steps, "batch_per_gpu": B,
            "config": {"workload": "%s: decode + select %.2f + top-k %d + NMS %.2f keep %d, BASELINE configs[%d]" % (
                name, SELECT_THR, TOP_K, NMS_THR, KEEP, 4 if stress else 2),
