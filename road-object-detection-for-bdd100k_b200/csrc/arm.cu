@@ -69,13 +69,8 @@ arm_jaccard_bigger_kernel(const __grid_constant__ Layout L, const __grid_constan
     t_ymin = fminf(t_ymin, a[u].x); t_xmin = fminf(t_xmin, a[u].y);
     t_ymax = fmaxf(t_ymax, a[u].z); t_xmax = fmaxf(t_xmax, a[u].w);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    t_ymin = fminf(t_ymin, __shfl_xor_sync(0xffffffffu, t_ymin, o));
-    t_xmin = fminf(t_xmin, __shfl_xor_sync(0xffffffffu, t_xmin, o));
-    t_ymax = fmaxf(t_ymax, __shfl_xor_sync(0xffffffffu, t_ymax, o));
-    t_xmax = fmaxf(t_xmax, __shfl_xor_sync(0xffffffffu, t_xmax, o));
-  }
+  t_ymin = warp_min(t_ymin); t_xmin = warp_min(t_xmin);
+  t_ymax = warp_max(t_ymax); t_xmax = warp_max(t_xmax);
   __syncthreads();
 
   // ---- per-anchor max / first-argmax over the GT boxes that can intersect this warp's anchors

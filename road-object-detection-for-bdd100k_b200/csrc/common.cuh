@@ -87,11 +87,26 @@ struct Thresholds {
 // ---------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------
+// layer of flat anchor n (< n_total).  to_layout() pads offset[i] = n_total for i > n_layers, so the
+// unused entries never count.
 __device__ __forceinline__ int layer_of(const Layout& L, int n) {
   int l = 0;
 #pragma unroll
-  for (int i = 1; i < ROD_MAX_LAYERS; ++i) l += (i < L.n_layers && n >= L.offset[i]) ? 1 : 0;
+  for (int i = 1; i < ROD_MAX_LAYERS; ++i) l += (n >= L.offset[i]) ? 1 : 0;
   return l;
+}
+
+// warp-wide min / max of a float through the integer REDUX unit (order-preserving key transform)
+__device__ __forceinline__ int float_order_key(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : (i ^ 0x7fffffff);
+}
+__device__ __forceinline__ float order_key_float(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+__device__ __forceinline__ float warp_min(float f) {
+  return order_key_float(__reduce_min_sync(0xffffffffu, float_order_key(f)));
+}
+__device__ __forceinline__ float warp_max(float f) {
+  return order_key_float(__reduce_max_sync(0xffffffffu, float_order_key(f)));
 }
 
 // centerBboxes_2_cornerBboxes, utils/common_tools.py:28-31 (h / 2 is exact in binary fp)

@@ -33,12 +33,25 @@ odm_target_kernel(const __grid_constant__ Layout L, const __grid_constant__ Thre
   const int lab = __ldg(lp1(labels, L, l, b, n));
   const int pm = __ldg(lp1(pos_mask, L, l, b, n));
   const float4 ac = ldg4(center + 4ll * n);
-  // :459-460 refined anchors, corner form ; :463 matched GT, corner form
-  const float4 ra = center_to_corner(decode_center(ac, ro));
-  const float4 gc = center_to_corner(cb);
-  // :465 element-wise jaccard(refined anchor, its assigned GT)
-  const float area_g = __fmul_rn(__fsub_rn(gc.z, gc.x), __fsub_rn(gc.w, gc.y));
-  const float j = jaccard_ref(ra, box_vol(ra), gc, area_g);
+  // Fast path for warps without any matched anchor (most of them).  An unmatched anchor carries
+  // cbboxes == (0,0,0,0), so its GT corner box is (0,0,0,0): the y-extent of the intersection is
+  // max(min(ymax,0) - max(ymin,0), 0) == 0 whatever the refined box is, hence inter == 0 and
+  // iou == 0 / vol_a == 0 exactly as long as vol_a is a positive finite number.  The bounds below
+  // guarantee that without evaluating exp(): h = exp(o2)*ah >= e^-2 * 2^-10 dwarfs the rounding of
+  // cy +- h/2 for |cy| <= 16, and e^40 * ah stays far from overflow.
+  const float cy = __fadd_rn(__fmul_rn(ro.x, ac.z), ac.x), cx = __fadd_rn(__fmul_rn(ro.y, ac.w), ac.y);
+  const bool trivial = cb.x == 0.f && cb.y == 0.f && cb.z == 0.f && cb.w == 0.f && ro.z >= -2.f && ro.z <= 40.f &&
+                       ro.w >= -2.f && ro.w <= 40.f && fabsf(cy) <= 16.f && fabsf(cx) <= 16.f &&
+                       ac.z >= 0.0009765625f && ac.w >= 0.0009765625f;
+  float j = 0.f;
+  if (!__all_sync(__activemask(), trivial)) {
+    // :459-460 refined anchors, corner form ; :463 matched GT, corner form
+    const float4 ra = center_to_corner(decode_center(ac, ro));
+    const float4 gc = center_to_corner(cb);
+    // :465 element-wise jaccard(refined anchor, its assigned GT)
+    const float area_g = __fmul_rn(__fsub_rn(gc.z, gc.x), __fsub_rn(gc.w, gc.y));
+    j = jaccard_ref(ra, box_vol(ra), gc, area_g);
+  }
   // :468-469
   const int m = ((j >= T.v[l]) ? 1 : 0) * pm;
   const float mf = (float)m;
