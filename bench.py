@@ -395,6 +395,9 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize(dev)
     fp32_nofma_tops = ops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    roofline["note"] = ("ARM is bound by FP32 non-FMA issue, not HBM: evaluating all 14*N*G pair flops at the measured "
+                        "FADD/FMUL rate would take %.1f us per launch; the step as a whole is graded against HBM "
+                        "(step_frac_of_hbm_roofline)" % (14.0 * N * mean_g * B / (fp32_nofma_tops * 1e12) * 1e6))
     roofline["fp32_nofma_tops_measured"] = fp32_nofma_tops
     roofline["arm_pair_flops_frac"] = (14.0 * N * mean_g * B / (ms_arm * 1e-3)) / (fp32_nofma_tops * 1e12)
 
@@ -421,7 +424,7 @@ def main():
         torch.cuda.current_stream(dev).synchronize()       # the caller reads the result
 
     e2e_steps = max(5, min(args.steps, 50))
-    ms_e2e = time_loop(step_e2e, e2e_steps, 3)
+    ms_e2e = float(np.median([time_loop(step_e2e, e2e_steps, 3) for _ in range(3)]))   # host / PCIe variance
     e2e = {"value": world * B * e2e_steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps,
            "api": "net_tools.refine_groundtruth + net_tools.det_groundtruth on pinned host inputs; "
@@ -514,8 +517,8 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
                "collective": "NCCL all_gather of [11,B] int32 detection counts" if world > 1 else "none (1 GPU)"},
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                         "frac": alg_bytes / (ms / steps * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes_per_step": alg_bytes,
-                        "scope": "whole step (top-k + NMS kernels)"},
-           "gpu_launches": 2 * steps, "detections_per_image": float(sets[0]["out"][2].sum().item()) / B}
+                        "scope": "whole step (scan + segment kernels)"},
+           "gpu_launches": 5 * steps, "kernels_per_step": ["scan_kernel<0,11>", "scan_kernel<1,11>", "segment_kernel", "topk_segment_kernel (overflow only)", "nms_kernel (overflow only)"], "detections_per_image": float(sets[0]["out"][2].sum().item()) / B}
 
     # e2e through the public API with pinned host inputs and results read back
     p, ro, do = sets[0]["host"]
@@ -539,7 +542,7 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
         torch.cuda.current_stream(dev).synchronize()
 
     e2e_steps = max(3, min(steps, 10))
-    ms_e = time_loop(step_e2e, e2e_steps, 2)
+    ms_e = float(np.median([time_loop(step_e2e, e2e_steps, 2) for _ in range(3)]))
     res["e2e"] = {"value": world * B * e2e_steps / (ms_e * 1e-3), "unit": "images/s", "ms_per_step": ms_e / e2e_steps,
                   "h2d_bytes_per_step": sum(x.numel() * 4 for x in h_p + h_ro + h_do),
                   "d2h_bytes_per_step": (h_s[1:].numel() + h_b[1:].numel()) * 4,
