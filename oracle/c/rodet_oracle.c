@@ -196,6 +196,15 @@ void orc_detect(const float* probs, const float* boxes, int batch, int n, int n_
   }
 }
 
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  extern void omp_set_num_threads(int);
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   extern int omp_get_max_threads(void);

@@ -33,6 +33,10 @@ def threads():
     return int(load().orc_max_threads())
 
 
+def set_threads(n):
+    load().orc_set_threads(int(n))
+
+
 def per_anchor_thresholds(table, thresholds):
     return np.ascontiguousarray(np.asarray(thresholds, dtype=np.float32)[table.layer_of])
 
