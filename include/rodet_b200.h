@@ -212,6 +212,17 @@ int rod_detect(const rod_layout_t* layout, const float* anchors_center,
                float* out_bboxes, int32_t* out_counts, void* workspace, size_t workspace_bytes,
                void* stream);
 
+/* ---- f-2  evaluation TP / FP matching ----------------------------------------------
+ * Replaces tfe.bboxes_matching / bboxes_matching_batch for one class
+ * (utils/tf_extended/bboxes.py:246-380): scores[rows,n] (unused by the matching itself, kept for
+ * signature parity), bboxes[rows,n,4] detections in score order; glabels[rows,g], gbboxes[rows,g,4],
+ * gdifficults[rows,g] (int64 if labels_i64 else int32; zero-padded GT has label 0).
+ * Outputs: out_n_gbboxes[rows] int64 (non-difficult GT of this class), out_tp / out_fp [rows,n] bool. */
+int rod_bboxes_matching_batch(int64_t label, const float* scores, const float* bboxes, const void* glabels,
+                              const float* gbboxes, const void* gdifficults, int labels_i64, int rows,
+                              int n, int g_n, float matching_threshold, int64_t* out_n_gbboxes,
+                              uint8_t* out_tp, uint8_t* out_fp, void* stream);
+
 /* ---- measurement helpers (bench.py) ------------------------------------------------
  * rod_peak_fp32_nofma: runs a dependent-chain FADD/FMUL (no FMA) kernel and returns in
  * *ops the number of FP32 instructions-lanes issued; time it with events on `stream`. */

@@ -467,3 +467,47 @@ def softmax(logits):
     a = np.asarray(logits, dtype=f32)
     e = np.exp(a - a.max(axis=-1, keepdims=True))
     return (e / e.sum(axis=-1, keepdims=True)).astype(f32)
+
+
+# --------------------------------------------------------------------------- #
+# f-2  eval TP/FP matching  (utils/tf_extended/bboxes.py:246-380)
+# --------------------------------------------------------------------------- #
+def bboxes_matching(label, scores, bboxes, glabels, gbboxes, gdifficults, matching_threshold=0.5):
+    """One image, one class: greedy matching of the detections (in the given order) to GT boxes.
+    Returns (n_gbboxes int64, tp[N] bool, fp[N] bool).  utils/tf_extended/bboxes.py:267-334."""
+    s = np.asarray(scores, dtype=f32).reshape(-1)
+    b = np.asarray(bboxes, dtype=f32).reshape(-1, 4)
+    gl = np.asarray(glabels)
+    gb = np.asarray(gbboxes, dtype=f32).reshape(-1, 4)
+    gd = np.asarray(gdifficults).astype(bool)
+    same = (gl == gl.dtype.type(label))
+    n_gb = np.int64(np.count_nonzero(same & ~gd))                        # :274-275
+    gmatch = np.zeros(gl.shape, dtype=bool)
+    tp = np.zeros(s.shape, dtype=bool)
+    fp = np.zeros(s.shape, dtype=bool)
+    for i in range(s.shape[0]):
+        jac = bboxes_jaccard(b[i], gb) * same.astype(f32)               # :292-293
+        idx = int(np.argmax(jac))                                        # :296 first max
+        match = jac[idx] > f32(matching_threshold)                       # :298
+        existing = gmatch[idx]
+        not_diff = not gd[idx]
+        tp[i] = not_diff and match and not existing                      # :304-305
+        fp[i] = not_diff and (existing or not match)                     # :307-308
+        if not_diff and match:                                           # :311-313
+            gmatch[idx] = True
+    return n_gb, tp, fp
+
+
+def bboxes_matching_batch(labels, scores, bboxes, glabels, gbboxes, gdifficults, matching_threshold=0.5):
+    """Batched / dict form (utils/tf_extended/bboxes.py:337-380): dict inputs return
+    (d_n_gbboxes, d_tp, d_fp, scores)."""
+    if isinstance(scores, dict):
+        d_n, d_tp, d_fp = {}, {}, {}
+        for c in labels:
+            d_n[c], d_tp[c], d_fp[c], _ = bboxes_matching_batch(c, scores[c], bboxes[c], glabels, gbboxes,
+                                                                  gdifficults, matching_threshold)
+        return d_n, d_tp, d_fp, scores
+    out = [bboxes_matching(labels, scores[i], bboxes[i], glabels[i], gbboxes[i], gdifficults[i], matching_threshold)
+           for i in range(len(scores))]
+    return (np.asarray([o[0] for o in out], dtype=np.int64), np.stack([o[1] for o in out]),
+            np.stack([o[2] for o in out]), scores)

@@ -312,9 +312,8 @@ def _build_tf_module():
     tf.ones = ones
 
     def range_(start, limit=None, delta=1, dtype=None, name=None):
-        return Tensor(np.arange(*( [_unwrap(start)] if limit is None
-                                   else [_unwrap(start), _unwrap(limit)]),
-                                _unwrap(delta), dtype=_dt(dtype) or np.int32))
+        lo, hi = (0, _unwrap(start)) if limit is None else (_unwrap(start), _unwrap(limit))
+        return Tensor(np.arange(lo, hi, _unwrap(delta), dtype=_dt(dtype) or np.int32))
     tf.range = range_
 
     def _red(fn):

@@ -11,7 +11,8 @@ import torch
 from ... import _abi
 
 __all__ = ["bboxes_sort_all_classes", "bboxes_sort", "bboxes_clip", "bboxes_resize", "bboxes_nms",
-           "bboxes_nms_batch", "bboxes_jaccard", "bboxes_intersection"]
+           "bboxes_nms_batch", "bboxes_jaccard", "bboxes_intersection", "bboxes_matching",
+           "bboxes_matching_batch"]
 
 
 def _f32(t, name):
@@ -134,3 +135,50 @@ def bboxes_nms_batch(scores, bboxes, nms_threshold=0.5, keep_top_k=200, scope=No
                                                         keep_top_k=keep_top_k)
         return d_scores, d_bboxes
     return _nms(scores, bboxes, nms_threshold, keep_top_k)
+
+
+def _matching(label, scores, bboxes, glabels, gbboxes, gdifficults, matching_threshold):
+    s = _f32(scores, "scores")
+    b = _f32(bboxes, "bboxes")
+    gb = _f32(gbboxes, "gbboxes")
+    gl = _abi.require_cuda(glabels, "glabels").contiguous()
+    gd = _abi.require_cuda(gdifficults, "gdifficults").to(gl.dtype).contiguous()
+    if gl.dtype not in (torch.int64, torch.int32):
+        raise ValueError("glabels must be int64 or int32")
+    if s.dim() != 2 or b.shape != s.shape + (4,) or gl.dim() != 2 or gb.shape != gl.shape + (4,) or \
+            gl.shape[0] != s.shape[0] or gd.shape != gl.shape:
+        raise ValueError("bboxes_matching_batch expects scores [B,N], bboxes [B,N,4], glabels / gdifficults [B,G], gbboxes [B,G,4]")
+    B, N = s.shape
+    G = gl.shape[1]
+    n_gb = torch.empty((B,), dtype=torch.int64, device=s.device)
+    tp = torch.empty((B, N), dtype=torch.bool, device=s.device)
+    fp = torch.empty((B, N), dtype=torch.bool, device=s.device)
+    with _abi.device_guard(s.device):
+        _abi.check(_abi.lib.rod_bboxes_matching_batch(int(label), s.data_ptr(), b.data_ptr(), gl.data_ptr(), gb.data_ptr(),
+                                                      gd.data_ptr(), 1 if gl.dtype == torch.int64 else 0, B, N, G,
+                                                      float(matching_threshold), n_gb.data_ptr(), tp.data_ptr(),
+                                                      fp.data_ptr(), _abi.stream_ptr(s.device)))
+    return n_gb, tp, fp
+
+
+def bboxes_matching(label, scores, bboxes, glabels, gbboxes, gdifficults, matching_threshold=0.5, scope=None):
+    """TP / FP matching of one image's detections of class `label` (in score order) against its
+    ground truth (utils/tf_extended/bboxes.py:246-334).  Returns (n_gbboxes, tp[N], fp[N])."""
+    n, tp, fp = _matching(label, scores.unsqueeze(0), bboxes.unsqueeze(0), glabels.unsqueeze(0),
+                          gbboxes.unsqueeze(0), gdifficults.unsqueeze(0), matching_threshold)
+    return n[0], tp[0], fp[0]
+
+
+def bboxes_matching_batch(labels, scores, bboxes, glabels, gbboxes, gdifficults, matching_threshold=0.5,
+                          scope=None):
+    """Batched / per-class-dict form (utils/tf_extended/bboxes.py:337-380); dict inputs return
+    (d_n_gbboxes, d_tp, d_fp, scores) like the reference."""
+    if isinstance(scores, dict) or isinstance(bboxes, dict):
+        d_n_gbboxes, d_tp, d_fp = {}, {}, {}
+        for c in labels:
+            n, tp, fp, _ = bboxes_matching_batch(c, scores[c], bboxes[c], glabels, gbboxes, gdifficults,
+                                                 matching_threshold)
+            d_n_gbboxes[c], d_tp[c], d_fp[c] = n, tp, fp
+        return d_n_gbboxes, d_tp, d_fp, scores
+    n, tp, fp = _matching(labels, scores, bboxes, glabels, gbboxes, gdifficults, matching_threshold)
+    return n, tp, fp, scores

@@ -226,3 +226,36 @@ def test_tfe_ops_vs_reference_fixture(rb):
     assert bit_equal(rb.nt.jaccard(_cuda(a, rb.dev), _cuda(g, rb.dev)).cpu().numpy(), R.jaccard(a, g))
     assert bit_equal(rb.nt.jaccard(_cuda(z["boxes"], rb.dev), _cuda(z["boxes"][::-1].copy(), rb.dev)).cpu().numpy(),
                      R.jaccard(z["boxes"], z["boxes"][::-1]))
+
+
+def test_eval_matching_vs_reference_fixture(rb):
+    """f-2: TP / FP matching (tfe.bboxes_matching_batch) against the reference fixture, dict and tensor forms."""
+    z = golden("eval_matching.npz")
+    cl = [int(c) for c in z["classes"]]
+    sc = {c: _cuda(z["scores_c%d" % c], rb.dev) for c in cl}
+    bx = {c: _cuda(z["bboxes_c%d" % c], rb.dev) for c in cl}
+    gl, gb, gd = _cuda(z["glabels"], rb.dev), _cuda(z["gbboxes"], rb.dev), _cuda(z["gdifficults"], rb.dev)
+    n, tp, fp, s2 = rb.tfe.bboxes_matching_batch(cl, sc, bx, gl, gb, gd, matching_threshold=float(z["thr"]))
+    assert s2 is sc
+    for c in cl:
+        assert n[c].dtype == torch.int64 and tp[c].dtype == torch.bool
+        assert np.array_equal(n[c].cpu().numpy(), z["n_c%d" % c])
+        assert np.array_equal(tp[c].cpu().numpy(), z["tp_c%d" % c])
+        assert np.array_equal(fp[c].cpu().numpy(), z["fp_c%d" % c])
+    c = cl[0]
+    n1, tp1, fp1 = rb.tfe.bboxes_matching(c, sc[c][1], bx[c][1], gl[1], gb[1], gd[1], matching_threshold=float(z["thr"]))
+    assert int(n1) == int(z["n_c%d" % c][1]) and np.array_equal(tp1.cpu().numpy(), z["tp_c%d" % c][1])
+    assert np.array_equal(fp1.cpu().numpy(), z["fp_c%d" % c][1])
+    # int32 ground-truth labels and a larger randomised case against the NumPy restatement
+    rng = np.random.default_rng(5)
+    B, N, G = 5, 200, 70
+    g_b = np.sort(rng.uniform(0, 1, size=(B, G, 2, 2)).astype(np.float32), axis=2).reshape(B, G, 4)
+    g_l = rng.integers(0, 4, size=(B, G)).astype(np.int32)
+    g_d = (rng.uniform(size=(B, G)) < 0.15).astype(np.int32)
+    d_b = (g_b[:, rng.integers(0, G, size=N)] + rng.normal(0, 0.01, size=(B, N, 4))).astype(np.float32)
+    d_s = np.sort(rng.uniform(0, 1, size=(B, N)).astype(np.float32), axis=1)[:, ::-1].copy()
+    n2, tp2, fp2, _ = rb.tfe.bboxes_matching_batch(2, _cuda(d_s, rb.dev), _cuda(d_b, rb.dev), _cuda(g_l, rb.dev),
+                                                   _cuda(g_b, rb.dev), _cuda(g_d, rb.dev))
+    o = R.bboxes_matching_batch(2, d_s, d_b, g_l, g_b, g_d)
+    assert np.array_equal(n2.cpu().numpy(), o[0]) and np.array_equal(tp2.cpu().numpy(), o[1])
+    assert np.array_equal(fp2.cpu().numpy(), o[2]) and o[1].sum() > 20

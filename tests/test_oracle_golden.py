@@ -191,3 +191,15 @@ def test_tfe_ops():
     assert np.array_equal(ns, z["nms_scores"]) and np.array_equal(nb, z["nms_bboxes"])
     ss, sb = R.bboxes_sort(s[None], b[None], 20)
     assert np.array_equal(ss, z["sort_scores"]) and np.array_equal(sb, z["sort_bboxes"])
+
+
+def test_eval_matching_restatement():
+    """f-2: tfe.bboxes_matching_batch restated, against the reference fixture."""
+    z = golden("eval_matching.npz")
+    cl = [int(c) for c in z["classes"]]
+    n, tp, fp, _ = R.bboxes_matching_batch(cl, {c: z["scores_c%d" % c] for c in cl}, {c: z["bboxes_c%d" % c] for c in cl},
+                                           z["glabels"], z["gbboxes"], z["gdifficults"], float(z["thr"]))
+    for c in cl:
+        assert np.array_equal(n[c], z["n_c%d" % c])
+        assert np.array_equal(tp[c], z["tp_c%d" % c]) and np.array_equal(fp[c], z["fp_c%d" % c])
+    assert sum(int(z["tp_c%d" % c].sum()) for c in cl) >= 8
