@@ -261,3 +261,59 @@ def test_detect_generic_class_count(env, monkeypatch):
     assert sorted(rs.keys()) == list(range(1, C))
     for c in range(1, C):
         assert bit_equal(rs[c].cpu().numpy(), o_s[c]) and bit_equal(rb[c].cpu().numpy(), o_b[c]), c
+
+
+def test_detect_large_topk_and_small_threshold(env):
+    """top_k = 800 (signature default, sort capacity 2048) with a low threshold: many candidates."""
+    assert _check_detect(env, "418", 700, 2, False, 0.05, 0.5, 800, 300) > 0
+    assert _check_detect(env, "512", 702, 1, True, 0.3, 0.45, 1000, 250) > 0
+
+
+def test_detect_batch_extremes(env):
+    """One image (64 scanning CTAs would be too many: clamped) and a large batch (256 images)."""
+    assert _check_detect(env, "512", 710, 1, False) > 0
+    layout, B = "418", 256
+    table = env.otable[layout]
+    probs, ro, do = _detect_inputs(env, layout, 720, 8, False)
+    probs, ro, do = (np.tile(a, (B // 8,) + (1,) * (a.ndim - 1)) for a in (probs, ro, do))
+    preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+    rs, rb = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=0.3,
+                                           nms_threshold=0.45, top_k=400, keep_top_k=200)
+    o_s, o_b = R.detected_bboxes(probs[:8], R.decode_corner(table, ro[:8], do[:8]), 0.3, 0.45, None, 400, 200)
+    for c in range(1, 11):
+        got_s, got_b = rs[c].cpu().numpy(), rb[c].cpu().numpy()
+        for rep in (0, 13, B // 8 - 1):
+            assert bit_equal(got_s[rep * 8:(rep + 1) * 8], o_s[c]) and bit_equal(got_b[rep * 8:(rep + 1) * 8], o_b[c])
+    # empty batch
+    e = lambda ts: [t[:0] for t in ts]
+    rs0, rb0 = env.nt.decode_detected_bboxes(env.anchors[layout], e(ro_l), e(do_l), e(preds), select_threshold=0.3)
+    assert rs0[1].shape == (0, 200) and rb0[1].shape == (0, 200, 4)
+
+
+def test_arm_gt_count_extremes(env):
+    """A single GT box, and more GT boxes than one 256-thread staging pass (gmax = 300)."""
+    layout = "418"
+    table = env.otable[layout]
+    JB = env.config.refine_method.JACCARD_BIGGER
+    rng = np.random.default_rng(3)
+    for G in (1, 300):
+        c = rng.uniform(0.1, 0.9, size=(2, G, 2))
+        hw = np.exp(rng.uniform(np.log(0.03), np.log(0.5), size=(2, G, 2)))
+        corner = np.clip(np.concatenate([c - hw / 2, c + hw / 2], -1), 0, 1).astype(np.float32)
+        center = R.corner_to_center(corner).astype(np.float32)
+        labels = rng.integers(1, 11, size=(2, G)).astype(np.int64)
+        counts = np.array([G, max(1, G // 2)], np.int32)
+        out = env.nt.refine_groundtruth(env.anchors[layout], torch.from_numpy(center).to(env.dev),
+                                        torch.from_numpy(labels).to(env.dev), JB,
+                                        gt_counts=torch.from_numpy(counts).to(env.dev), return_match_index=True)
+        g = [flat_from_list(x, t) for x, t in zip(out, (1, 1, 1, 1, 0))]
+        for b in range(2):
+            o = R.arm_match_encode(table, center[b, :counts[b]], labels[b, :counts[b]])
+            assert np.array_equal(g[3][b, :, 0], o[3]) and np.array_equal(g[4][b], o[4])
+            assert bit_equal(g[0][b], o[0]) and bit_equal(g[1][b], o[1]) and np.array_equal(g[2][b, :, 0], o[2])
+    # per-image (reference) form == batched form
+    one = env.nt.refine_groundtruth(env.anchors[layout], torch.from_numpy(center[0]).to(env.dev),
+                                    torch.from_numpy(labels[0]).to(env.dev), JB)
+    assert tuple(one[0][0].shape) == table.shapes[0] + (4,)
+    assert bit_equal(flat_from_list([t.unsqueeze(0) for t in one[0]], 1)[0], g[0][0])
