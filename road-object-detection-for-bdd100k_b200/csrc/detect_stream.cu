@@ -32,7 +32,7 @@ constexpr int kSegWarps = kSegBlock / 32;
 
 __device__ __forceinline__ int score_bin(float s) {
   // monotone non-decreasing in s for s > 0; only resolution (never correctness) depends on it
-  return s >= 1.f ? (kBins - 1) : (int)(s * (float)kBins);
+  return min((int)(s * (float)kBins), kBins - 1);     // float -> int conversion saturates, NaN -> 0
 }
 
 // Walks the float range [F0, F1) of image b's concatenated [N*C] score array (layer-major),
@@ -166,6 +166,7 @@ struct ScanShared {
   unsigned hist[MODE == 0 ? C * kBins / 2 : 1];                 // two 16-bit counters per word
   unsigned cnt[C];
   int tb[C];
+  unsigned long long* slice[C];                                 // MODE 0: this CTA's list slice per class
 };
 
 // One anchor per lane; `row` points at its C scores (shared-memory tile, or global for the few
@@ -191,15 +192,15 @@ __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE
     cand &= cand - 1;
     const float s = row[c];
     const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | nkey;
-    const size_t r = (size_t)c * P.batch + b;
     if constexpr (MODE == 0) {
       const int bin = score_bin(s);
-      atomicAdd(&S.hist[(c * kBins + bin) >> 1], 1u << ((bin & 1) << 4));
+      atomicAdd(&S.hist[c * (kBins / 2) + (bin >> 1)], 1u << ((bin & 1) << 4));
       if (S.cnt[c] < (unsigned)P.spc) {
         const unsigned pos = atomicAdd(&S.cnt[c], 1u);
-        if (pos < (unsigned)P.spc) P.g_list[r * kListCap + (size_t)blockIdx.x * P.spc + pos] = key;
+        if (pos < (unsigned)P.spc) S.slice[c][pos] = key;
       }
     } else {
+      const size_t r = (size_t)c * P.batch + b;
       const unsigned pos = atomicAdd(&P.g_cnt2[r], 1u);
       if (pos < (unsigned)P.cap2) P.g_list2[r * P.cap2 + pos] = key;
     }
@@ -222,7 +223,10 @@ scan_kernel(const __grid_constant__ ScanParams P) {
   }
   if (tid == 0) s_any = 0;
   __syncthreads();
-  if (tid < C) S.cnt[tid] = 0u;
+  if (tid < C) {
+    S.cnt[tid] = 0u;
+    S.slice[tid] = P.g_list + ((size_t)tid * P.batch + b) * kListCap + (size_t)blockIdx.x * P.spc;
+  }
   if constexpr (MODE == 1) {
     // threshold bins of this image's dense classes, straight from the finished histograms
     for (int c = tid >> 5; c < C; c += kScanBlock / 32) {
