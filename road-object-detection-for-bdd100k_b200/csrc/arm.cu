@@ -17,7 +17,7 @@
 
 namespace rod {
 
-constexpr int kArmBlock = 256;
+constexpr int kArmBlock = 128;
 
 constexpr int kArmPer = 1;                               // anchors per lane (2 measured slower on B200: 41 us vs 35 us at B=32)
 constexpr int kArmTile = kArmBlock * kArmPer;
