@@ -651,13 +651,18 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     return ok ? make_float4(__fadd_rn(c.x, sh), __fadd_rn(c.y, sw), __fsub_rn(c.z, sh), __fsub_rn(c.w, sw)) : c;
   };
   int nk = 0;
-  for (int p0 = 0; p0 < m && nk < keep; p0 += 64) {
-    const int nb = min(64, m - p0);
+  int bsz = 64;
+  for (int p0 = 0; p0 < m && nk < keep; p0 += bsz) {
+    // close to keep_top_k a half batch (one candidate per lane) is enough: the last full batch would
+    // spend a quarter of all pair tests on a handful of survivors
+    bsz = (keep - nk <= 24) ? 32 : 64;
+    const bool two = bsz == 64;
+    const int nb = min(bsz, m - p0);
     const int c0 = p0 + lane, c1 = c0 + 32;
-    const float4 b0 = c0 < m ? s_nbox[c0] : none;
-    const float4 b1 = c1 < m ? s_nbox[c1] : none;
-    const float a0 = c0 < m ? s_area[c0] : 0.f, a1 = c1 < m ? s_area[c1] : 0.f;
-    const float4 q0 = shrunk(b0, a0), q1 = shrunk(b1, a1);
+    const bool v1 = two && c1 < m;
+    // only the shrunk boxes stay in registers; the IoU tests (rare) re-read box and area
+    const float4 q0 = c0 < m ? shrunk(s_nbox[c0], s_area[c0]) : none;
+    const float4 q1 = v1 ? shrunk(s_nbox[c1], s_area[c1]) : none;
     if (tid == 0) s_dead = 0ull;
     // -- vs the kept list: warp w takes rows w, w+8, ...  First a branch-free pass that only records
     // which rows intersect the lane's candidates (pipelined broadcast loads + compares), then the
@@ -666,21 +671,29 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     for (int jb = warp; jb < nk; jb += 32 * kSegWarps) {
       unsigned h0 = 0u, h1 = 0u;
       const int ni = min(32, (nk - jb + kSegWarps - 1) / kSegWarps);      // rows of this pass (warp-uniform)
+      if (two) {
 #pragma unroll 4
-      for (int i = 0; i < ni; ++i) {
-        const float4 kb = s_kbox[jb + i * kSegWarps];
-        h0 |= (unsigned)((kb.z > q0.x) && (q0.z > kb.x) && (kb.w > q0.y) && (q0.w > kb.y)) << i;
-        h1 |= (unsigned)((kb.z > q1.x) && (q1.z > kb.x) && (kb.w > q1.y) && (q1.w > kb.y)) << i;
+        for (int i = 0; i < ni; ++i) {
+          const float4 kb = s_kbox[jb + i * kSegWarps];
+          h0 |= (unsigned)((kb.z > q0.x) && (q0.z > kb.x) && (kb.w > q0.y) && (q0.w > kb.y)) << i;
+          h1 |= (unsigned)((kb.z > q1.x) && (q1.z > kb.x) && (kb.w > q1.y) && (q1.w > kb.y)) << i;
+        }
+      } else {
+#pragma unroll 4
+        for (int i = 0; i < ni; ++i) {
+          const float4 kb = s_kbox[jb + i * kSegWarps];
+          h0 |= (unsigned)((kb.z > q0.x) && (q0.z > kb.x) && (kb.w > q0.y) && (q0.w > kb.y)) << i;
+        }
       }
       while (h0 && !d0) {
         const int j = jb + (__ffs(h0) - 1) * kSegWarps;
         h0 &= h0 - 1;
-        d0 = suppresses(s_kbox[j], s_karea[j], b0, a0);
+        d0 = suppresses(s_kbox[j], s_karea[j], s_nbox[c0], s_area[c0]);
       }
       while (h1 && !d1) {
         const int j = jb + (__ffs(h1) - 1) * kSegWarps;
         h1 &= h1 - 1;
-        d1 = suppresses(s_kbox[j], s_karea[j], b1, a1);
+        d1 = suppresses(s_kbox[j], s_karea[j], s_nbox[c1], s_area[c1]);
       }
     }
     // -- vs the batch itself: warp w takes rows 8w .. 8w+7; bit i of cm = row 8w+i suppresses my column
@@ -693,19 +706,20 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
         const int rrow = r0 + rr;                       // warp-uniform
         if (rrow < nb) {
           const float4 bi = s_nbox[p0 + rrow];
-          h0 |= (unsigned)(lane > rrow && (bi.z > q0.x) && (q0.z > bi.x) && (bi.w > q0.y) && (q0.w > bi.y)) << rr;
-          h1 |= (unsigned)(lane + 32 > rrow && (bi.z > q1.x) && (q1.z > bi.x) && (bi.w > q1.y) && (q1.w > bi.y)) << rr;
+          // rows >= 32 can only suppress the second candidate; a half batch has no second candidate
+          if (rrow < 32) h0 |= (unsigned)(lane > rrow && (bi.z > q0.x) && (q0.z > bi.x) && (bi.w > q0.y) && (q0.w > bi.y)) << rr;
+          if (two) h1 |= (unsigned)(lane + 32 > rrow && (bi.z > q1.x) && (q1.z > bi.x) && (bi.w > q1.y) && (q1.w > bi.y)) << rr;
         }
       }
       while (h0) {
         const int rr = __ffs(h0) - 1;
         h0 &= h0 - 1;
-        cm0 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], b0, a0) << rr;
+        cm0 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], s_nbox[c0], s_area[c0]) << rr;
       }
       while (h1) {
         const int rr = __ffs(h1) - 1;
         h1 &= h1 - 1;
-        cm1 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], b1, a1) << rr;
+        cm1 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], s_nbox[c1], s_area[c1]) << rr;
       }
     }
     s_cmw[lane * kSegWarps + warp] = cm0;
@@ -750,11 +764,11 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
       // append the survivors to the kept list, in order (lane owns candidates lane and lane + 32)
       if ((K >> lane) & 1ull) {
         const int pos = nk + __popcll(K & ((1ull << lane) - 1ull));
-        s_selected[pos] = c0; s_kbox[pos] = b0; s_karea[pos] = a0;
+        s_selected[pos] = c0; s_kbox[pos] = s_nbox[c0]; s_karea[pos] = s_area[c0];
       }
       if ((K >> (lane + 32)) & 1ull) {
         const int pos = nk + __popcll(K & ((1ull << (lane + 32)) - 1ull));
-        s_selected[pos] = c1; s_kbox[pos] = b1; s_karea[pos] = a1;
+        s_selected[pos] = c1; s_kbox[pos] = s_nbox[c1]; s_karea[pos] = s_area[c1];
       }
       if (lane == 0) s_sel = K;
     }
