@@ -430,8 +430,14 @@ struct SegParams {
 };
 
 // bytes of the aliased region: sort keys, later {kept boxes, overlap words, batch rows, kept areas}
-__host__ __device__ inline size_t seg_region_a(int cap, int keep) {
-  const size_t a = (size_t)cap * 16 + 1024 * 4, b = (size_t)keep * (16 + 4) + 64 * 8 * 4;
+// offset of the shrunk candidate boxes inside region A: behind the NMS working set and behind the
+// first k sort keys (still being read while the gather phase writes them)
+__host__ __device__ inline size_t seg_qbox_offset(int k, int keep) {
+  const size_t b = (size_t)keep * (16 + 4) + 64 * 8 * 4, c = (size_t)k * 8;
+  return ((b > c ? b : c) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t seg_region_a(int cap, int k, int keep) {
+  const size_t a = (size_t)cap * 16 + 1024 * 4, b = seg_qbox_offset(k, keep) + (size_t)k * 16;
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
@@ -458,11 +464,12 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   //           (kept boxes, kept areas, overlap words, intra-batch rows)
   // then: boxes (k x 16), normalised boxes (k x 16), area, score (k x 4 each), kept positions (keep x 4)
   const int cap = P.cap, k = P.k, keep = P.keep;
-  const size_t regionA = seg_region_a(cap, keep);
+  const size_t regionA = seg_region_a(cap, k, keep);
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_raw);
   float4* s_kbox = reinterpret_cast<float4*>(s_raw);                                   // [keep] kept boxes
   unsigned* s_cmw = reinterpret_cast<unsigned*>(s_kbox + keep);                        // [64][kSegWarps] partial column masks
   float* s_karea = reinterpret_cast<float*>(s_cmw + 64 * kSegWarps);                   // [keep] kept areas
+  float4* s_qbox = reinterpret_cast<float4*>(s_raw + seg_qbox_offset(k, keep));       // [k] shrunk candidate boxes (NMS predicate)
   float4* s_box = reinterpret_cast<float4*>(s_raw + regionA);
   float4* s_nbox = s_box + k;
   float* s_area = reinterpret_cast<float*>(s_nbox + k);
@@ -595,6 +602,20 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   SEG_T(2);
   const int m = min(cnt, k);                          // real candidates entering NMS
 
+  const float thr = P.nms_thr;
+  // Pair predicate.  iou > thr needs inter > thr * max(area_r, area_c), hence an overlap of more
+  // than thr * h_c in y and thr * w_c in x (inter <= ih * w_c and inter <= h_c * iw, in the rounded
+  // arithmetic too: fl() is monotone).  So the candidate's box shrunk by 0.99 * thr * (h, w) on every
+  // side must still intersect the row: the same four compares as the plain intersection test, ~3x
+  // fewer IoU evaluations.  The 1 % slack covers the rounding of the shrunk corners as long as the
+  // coordinates are < 2^16 times the shrink; otherwise the plain box is used.
+  const float tq = __fmul_rn(thr, 0.99f);
+  auto shrunk = [&](const float4& c, float area) -> float4 {
+    const float sh = __fmul_rn(tq, __fsub_rn(c.z, c.x)), sw = __fmul_rn(tq, __fsub_rn(c.w, c.y));
+    const bool ok = area > 1e-30f && fmaxf(fabsf(c.x), fabsf(c.z)) < __fmul_rn(65536.f, sh) &&
+                    fmaxf(fabsf(c.y), fabsf(c.w)) < __fmul_rn(65536.f, sw);
+    return ok ? make_float4(__fadd_rn(c.x, sh), __fadd_rn(c.y, sw), __fsub_rn(c.z, sh), __fsub_rn(c.w, sw)) : c;
+  };
   // ---- 2. gather / decode the m boxes (evaluate.py:141-142), select-stage mask is 1 for all of them
   for (int j = tid; j < m; j += kSegBlock) {
     const unsigned long long key = s_keys[j];
@@ -614,7 +635,9 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     const float area = __fmul_rn(__fsub_rn(nb.z, nb.x), __fsub_rn(nb.w, nb.y));
     s_box[j] = v;
     // boxes with area <= 0 never overlap anything (TF IOU returns 0): make them unreachable
-    s_nbox[j] = (area > 0.f) ? nb : make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    const float4 nbv = (area > 0.f) ? nb : make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    s_nbox[j] = nbv;
+    s_qbox[j] = shrunk(nbv, area);
     s_area[j] = area;
     s_score[j] = __uint_as_float((unsigned)(key >> 32));
   }
@@ -628,7 +651,6 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   // shared memory; exact 4-compare intersection predicate, IoU only when it holds) and against the
   // batch rows of its warp, accumulating "dead" bits and per-column suppressor masks in registers.
   // Phase 2 (warp 0): resolve the 64 x 64 intra-batch dependencies and append the survivors.
-  const float thr = P.nms_thr;
   const float4 none = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
   auto suppresses = [&](const float4& r, float ar, const float4& c, float ac) -> bool {
     const float ih = __fsub_rn(fminf(r.z, c.z), fmaxf(r.x, c.x));
@@ -636,19 +658,6 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     const float inter = __fmul_rn(ih, iw);
     const float den = __fsub_rn(__fadd_rn(ar, ac), inter);
     return (thr >= 0.f && den > 1e-30f) ? iou_exceeds(inter, den, thr) : (__fdiv_rn(inter, den) > thr);
-  };
-  // Pair predicate.  iou > thr needs inter > thr * max(area_r, area_c), hence an overlap of more
-  // than thr * h_c in y and thr * w_c in x (inter <= ih * w_c and inter <= h_c * iw, in the rounded
-  // arithmetic too: fl() is monotone).  So the candidate's box shrunk by 0.99 * thr * (h, w) on every
-  // side must still intersect the row: the same four compares as the plain intersection test, ~3x
-  // fewer IoU evaluations.  The 1 % slack covers the rounding of the shrunk corners as long as the
-  // coordinates are < 2^16 times the shrink; otherwise the plain box is used.
-  const float tq = __fmul_rn(thr, 0.99f);
-  auto shrunk = [&](const float4& c, float area) -> float4 {
-    const float sh = __fmul_rn(tq, __fsub_rn(c.z, c.x)), sw = __fmul_rn(tq, __fsub_rn(c.w, c.y));
-    const bool ok = area > 1e-30f && fmaxf(fabsf(c.x), fabsf(c.z)) < __fmul_rn(65536.f, sh) &&
-                    fmaxf(fabsf(c.y), fabsf(c.w)) < __fmul_rn(65536.f, sw);
-    return ok ? make_float4(__fadd_rn(c.x, sh), __fadd_rn(c.y, sw), __fsub_rn(c.z, sh), __fsub_rn(c.w, sw)) : c;
   };
   int nk = 0;
   int bsz = 64;
@@ -660,9 +669,10 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     const int nb = min(bsz, m - p0);
     const int c0 = p0 + lane, c1 = c0 + 32;
     const bool v1 = two && c1 < m;
-    // only the shrunk boxes stay in registers; the IoU tests (rare) re-read box and area
-    const float4 q0 = c0 < m ? shrunk(s_nbox[c0], s_area[c0]) : none;
-    const float4 q1 = v1 ? shrunk(s_nbox[c1], s_area[c1]) : none;
+    // only the shrunk boxes (computed once in the gather phase) stay in registers; the IoU tests
+    // (rare) re-read box and area
+    const float4 q0 = c0 < m ? s_qbox[c0] : none;
+    const float4 q1 = v1 ? s_qbox[c1] : none;
     if (tid == 0) s_dead = 0ull;
     // -- vs the kept list: warp w takes rows w, w+8, ...  First a branch-free pass that only records
     // which rows intersect the lane's candidates (pipelined broadcast loads + compares), then the
@@ -813,7 +823,7 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
 static long long* g_seg_dbg = nullptr;
 
 static size_t seg_smem_bytes(int cap, int k, int keep) {
-  return seg_region_a(cap, keep) + (size_t)k * (16 + 16 + 4 + 4) + (size_t)keep * 4 + 16;
+  return seg_region_a(cap, k, keep) + (size_t)k * (16 + 16 + 4 + 4) + (size_t)keep * 4 + 16;
 }
 static int stream_cap(int k) {
   int p = 1;
