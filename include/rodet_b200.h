@@ -212,6 +212,22 @@ int rod_detect(const rod_layout_t* layout, const float* anchors_center,
                float* out_bboxes, int32_t* out_counts, void* workspace, size_t workspace_bytes,
                void* stream);
 
+/* ---- f-1  softmax in front of the select stage -----------------------------------------
+ * rod_softmax replaces slim.softmax(clf_out[i]) (evaluate.py:136-137, predict.py:127-128) for one
+ * [rows, n_classes] tensor (in place allowed).  rod_detect_logits is rod_detect with the class
+ * LOGITS as `logits`: the softmax is fused into the select pass (no probability tensor is written);
+ * its result is bit-identical to rod_softmax followed by rod_detect.  Probabilities follow the
+ * float32 softmax to < 1e-6 relative (hardware ex2), i.e. tolerance parity with the reference.
+ * Same workspace as rod_detect. */
+int rod_softmax(const float* logits, int64_t rows, int n_classes, float* out, void* stream);
+int rod_detect_logits(const rod_layout_t* layout, const float* anchors_center,
+                      const rod_layered_t* logits, const rod_layered_t* localizations,
+                      const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
+                      int n_classes, int ignore_class, float select_threshold, float nms_threshold,
+                      int top_k, int keep_top_k, const float* clip_box, float* out_scores,
+                      float* out_bboxes, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ---- f-2  evaluation TP / FP matching ----------------------------------------------
  * Replaces tfe.bboxes_matching / bboxes_matching_batch for one class
  * (utils/tf_extended/bboxes.py:246-380): scores[rows,n] (unused by the matching itself, kept for
@@ -267,6 +283,17 @@ int rod_dl_detect(const rod_layout_t* layout, const struct DLTensor* anchors_cen
                   int keep_top_k, const struct DLTensor* clip_box, const struct DLTensor* out_scores,
                   const struct DLTensor* out_bboxes, const struct DLTensor* out_counts,
                   const struct DLTensor* workspace, void* stream);
+
+/* rod_dl_detect with class logits (see rod_detect_logits); rod_dl_softmax: out may alias logits. */
+int rod_dl_detect_logits(const rod_layout_t* layout, const struct DLTensor* anchors_center,
+                         const struct DLTensor* const* logits,
+                         const struct DLTensor* const* localizations,
+                         const struct DLTensor* const* refine_out, const struct DLTensor* const* det_out,
+                         int ignore_class, float select_threshold, float nms_threshold, int top_k,
+                         int keep_top_k, const struct DLTensor* clip_box, const struct DLTensor* out_scores,
+                         const struct DLTensor* out_bboxes, const struct DLTensor* out_counts,
+                         const struct DLTensor* workspace, void* stream);
+int rod_dl_softmax(const struct DLTensor* logits, const struct DLTensor* out, void* stream);
 
 #ifdef __cplusplus
 }

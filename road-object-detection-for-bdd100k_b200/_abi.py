@@ -64,6 +64,10 @@ SIGNATURES = {
     "rod_dl_odm_target": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_dl_decode": (_i, [_LP, _vp, _vp, _vp, _i, _vp, _vp]),
     "rod_dl_detect": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rod_softmax": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "rod_detect_logits": (_i, [_LP, _vp, _YP, _YP, _YP, _YP, _i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rod_dl_detect_logits": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rod_dl_softmax": (_i, [_vp, _vp, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)       # AttributeError here = header and library out of sync

@@ -166,12 +166,12 @@ extern "C" int rod_dl_decode(const rod_layout_t* layout, const DLTensor* anchors
                     (float*)dl_ptr(out), stream);
 }
 
-extern "C" int rod_dl_detect(const rod_layout_t* layout, const DLTensor* anchors_center,
+static int dl_detect_impl(const rod_layout_t* layout, const DLTensor* anchors_center,
                              const DLTensor* const* predictions, const DLTensor* const* localizations,
                              const DLTensor* const* refine_out, const DLTensor* const* det_out, int ignore_class,
                              float select_threshold, float nms_threshold, int top_k, int keep_top_k,
                              const DLTensor* clip_box, const DLTensor* out_scores, const DLTensor* out_bboxes,
-                             const DLTensor* out_counts, const DLTensor* workspace, void* stream) {
+                             const DLTensor* out_counts, const DLTensor* workspace, void* stream, int logits) {
   int rc = check_layout(layout);
   if (rc) return rc;
   const int64_t N = layout->n_total;
@@ -196,10 +196,44 @@ extern "C" int rod_dl_detect(const rod_layout_t* layout, const DLTensor* anchors
   if (out_counts && (rc = dl_flat(out_counts, "out_counts", ROD_kDLInt, 32, (int64_t)C * B))) return rc;
   if ((rc = dl_check(workspace, "workspace", ROD_kDLUInt, 8))) return rc;
   DL_REQUIRE(dl_compact(workspace, 0), "workspace: must be contiguous");
-  return rod_detect(layout, anchors_center ? (const float*)dl_ptr(anchors_center) : nullptr, &pr,
+  return (logits ? rod_detect_logits : rod_detect)(layout, anchors_center ? (const float*)dl_ptr(anchors_center) : nullptr, &pr,
                     localizations ? &lo : nullptr, localizations ? nullptr : &ro, localizations ? nullptr : &dt, B, C,
                     ignore_class, select_threshold, nms_threshold, top_k, keep_top_k,
                     clip_box ? (const float*)dl_ptr(clip_box) : nullptr, (float*)dl_ptr(out_scores),
                     (float*)dl_ptr(out_bboxes), out_counts ? (int32_t*)dl_ptr(out_counts) : nullptr, dl_ptr(workspace),
                     (size_t)dl_numel(workspace), stream);
+}
+
+extern "C" int rod_dl_detect(const rod_layout_t* layout, const DLTensor* anchors_center,
+                             const DLTensor* const* predictions, const DLTensor* const* localizations,
+                             const DLTensor* const* refine_out, const DLTensor* const* det_out, int ignore_class,
+                             float select_threshold, float nms_threshold, int top_k, int keep_top_k,
+                             const DLTensor* clip_box, const DLTensor* out_scores, const DLTensor* out_bboxes,
+                             const DLTensor* out_counts, const DLTensor* workspace, void* stream) {
+  return dl_detect_impl(layout, anchors_center, predictions, localizations, refine_out, det_out, ignore_class,
+                        select_threshold, nms_threshold, top_k, keep_top_k, clip_box, out_scores, out_bboxes, out_counts,
+                        workspace, stream, 0);
+}
+
+extern "C" int rod_dl_detect_logits(const rod_layout_t* layout, const DLTensor* anchors_center,
+                                    const DLTensor* const* logits, const DLTensor* const* localizations,
+                                    const DLTensor* const* refine_out, const DLTensor* const* det_out, int ignore_class,
+                                    float select_threshold, float nms_threshold, int top_k, int keep_top_k,
+                                    const DLTensor* clip_box, const DLTensor* out_scores, const DLTensor* out_bboxes,
+                                    const DLTensor* out_counts, const DLTensor* workspace, void* stream) {
+  return dl_detect_impl(layout, anchors_center, logits, localizations, refine_out, det_out, ignore_class,
+                        select_threshold, nms_threshold, top_k, keep_top_k, clip_box, out_scores, out_bboxes, out_counts,
+                        workspace, stream, 1);
+}
+
+extern "C" int rod_dl_softmax(const DLTensor* logits, const DLTensor* out, void* stream) {
+  int rc;
+  if ((rc = dl_check(logits, "logits", ROD_kDLFloat, 32))) return rc;
+  if ((rc = dl_check(out, "out", ROD_kDLFloat, 32))) return rc;
+  DL_REQUIRE(logits->ndim >= 1, "logits: needs at least 1 dim");
+  DL_REQUIRE(dl_compact(logits, 0) && dl_compact(out, 0), "logits / out: must be contiguous");
+  const int64_t C = logits->shape[logits->ndim - 1], total = dl_numel(logits);
+  DL_REQUIRE(dl_numel(out) == total, "out: %lld elements, logits has %lld", (long long)dl_numel(out), (long long)total);
+  DL_REQUIRE(C >= 1 && C <= ROD_MAX_CLASSES, "logits: last dim (classes) = %lld not in [1,%d]", (long long)C, ROD_MAX_CLASSES);
+  return rod_softmax((const float*)dl_ptr(logits), C ? total / C : 0, (int)C, (float*)dl_ptr(out), stream);
 }

@@ -135,6 +135,24 @@ __device__ __forceinline__ float jaccard_ref(float4 a, float vol_a, float4 g, fl
 __device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float log_cr(float x) { return (float)log((double)x); }
 
+// slim.softmax over the class axis (evaluate.py:136-137, predict.py:127-128), one definition for the
+// stand-alone kernel, the fused select and the general fallback so that all three produce the same
+// bits: e_c = ex2((x_c - max) * log2(e)) with the hardware ex2 (2 ulp), s = e_0 + e_1 + ... in class
+// order, p_c = e_c * (1 / s).  Relative error vs an exact softmax < 1e-6 (tests: tolerance 1e-5).
+__device__ __forceinline__ float softmax_exp(float x, float m) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(__fsub_rn(x, m), 1.44269504088896340736f)));
+  return r;
+}
+// probability of class c of one row of n logits (generic class count; used by the fallback path)
+__device__ __forceinline__ float softmax_pick(const float* __restrict__ row, int n, int c) {
+  float m = __ldg(row);
+  for (int j = 1; j < n; ++j) m = fmaxf(m, __ldg(row + j));
+  float s = softmax_exp(__ldg(row), m);
+  for (int j = 1; j < n; ++j) s = __fadd_rn(s, softmax_exp(__ldg(row + j), m));
+  return __fmul_rn(softmax_exp(__ldg(row + c), m), __frcp_rn(s));
+}
+
 // decode_locations_one_layer, utils/net_tools.py:226-229 (a = acy,acx,ah,aw)
 __device__ __forceinline__ float4 decode_center(float4 a, float4 o) {
   return make_float4(__fadd_rn(__fmul_rn(o.x, a.z), a.x), __fadd_rn(__fmul_rn(o.y, a.w), a.y),

@@ -172,17 +172,42 @@ struct ScanShared {
 // One anchor per lane; `row` points at its C scores (shared-memory tile, or global for the few
 // unaligned head / tail anchors).  MODE 0: histogram + append to this CTA's private slice of the
 // segment's list while it has room.  MODE 1: append candidates at or above the threshold bin.
-template <int MODE, int C>
+// LOGITS: the row holds logits; probabilities come from softmax_exp / __frcp_rn (common.cuh), and a
+// candidate's probability is recomputed with the same instructions when its key is built.
+template <int MODE, int C, bool LOGITS>
 __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE, C>& S, bool valid,
                                             const float* __restrict__ row, int n, int b) {
   unsigned cand = 0;
+  float mx = 0.f, rinv = 0.f;
   if (valid) {
+    if constexpr (LOGITS) {
+      float e[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float s = row[c];
-      bool p = s >= P.thr;
-      if constexpr (MODE == 1) p = p && score_bin(s) >= S.tb[c];
-      cand |= (unsigned)p << c;
+      for (int c = 0; c < C; ++c) e[c] = row[c];
+      mx = e[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, e[c]);
+#pragma unroll
+      for (int c = 0; c < C; ++c) e[c] = softmax_exp(e[c], mx);
+      float sum = e[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) sum = __fadd_rn(sum, e[c]);
+      rinv = __frcp_rn(sum);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float s = __fmul_rn(e[c], rinv);
+        bool p = s >= P.thr;
+        if constexpr (MODE == 1) p = p && score_bin(s) >= S.tb[c];
+        cand |= (unsigned)p << c;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float s = row[c];
+        bool p = s >= P.thr;
+        if constexpr (MODE == 1) p = p && score_bin(s) >= S.tb[c];
+        cand |= (unsigned)p << c;
+      }
     }
     cand &= ~(1u << P.ignore_class);
   }
@@ -190,7 +215,8 @@ __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE
   while (cand) {
     const int c = __ffs(cand) - 1;
     cand &= cand - 1;
-    const float s = row[c];
+    float s = row[c];
+    if constexpr (LOGITS) s = __fmul_rn(softmax_exp(s, mx), rinv);
     const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | nkey;
     if constexpr (MODE == 0) {
       const int bin = score_bin(s);
@@ -207,7 +233,7 @@ __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE
   }
 }
 
-template <int MODE, int C>
+template <int MODE, int C, bool LOGITS>
 __global__ void __launch_bounds__(kScanBlock)
 scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -274,7 +300,7 @@ scan_kernel(const __grid_constant__ ScanParams P) {
     const int nscalar = (t0 - lo) + (hi - t1);
     for (int i = tid; i < nscalar; i += kScanBlock) {
       const int n = i < t0 - lo ? lo + i : t1 + (i - (t0 - lo));
-      scan_anchor<MODE, C>(P, S, true, slab + (long long)n * C, n, b);
+      scan_anchor<MODE, C, LOGITS>(P, S, true, slab + (long long)n * C, n, b);
     }
     for (int t = 0; t < ntiles; ++t) {
       const int q = t % kScanStages;
@@ -285,7 +311,7 @@ scan_kernel(const __grid_constant__ ScanParams P) {
       mbar_wait(&s_bar[q], (phases >> q) & 1u);
       phases ^= 1u << q;
       // row stride C words: conflict-free across lanes for odd C
-      scan_anchor<MODE, C>(P, S, tid < cnt, s_tiles + q * kScanBlock * C + tid * C, a0 + tid, b);
+      scan_anchor<MODE, C, LOGITS>(P, S, tid < cnt, s_tiles + q * kScanBlock * C + tid * C, a0 + tid, b);
       __syncthreads();                                   // tile consumed: its buffer may be refilled
     }
   }
@@ -842,10 +868,11 @@ size_t stream_workspace_bytes(int batch, int n_classes, int top_k) {
 // Enqueues A1, T, A2, B.  *over_out (device, [rows]) is non-zero for segments the exact general
 // kernels must redo.
 int launch_detect_stream(const Layout& L, const float* anchors_center, const LayeredF& probs, const LayeredF* loc,
-                         const LayeredF* refine, const LayeredF* det, int batch, int C, int ignore_class,
+                         const LayeredF* refine, const LayeredF* det, int batch, int C, int logits, int ignore_class,
                          float select_thr, float nms_thr, int top_k, int keep, const float* clip, float* out_scores,
                          float* out_boxes, int32_t* out_counts, void* ws, const unsigned** over_out, int* cap_out,
                          cudaStream_t st) {
+  ROD_REQUIRE(!logits || C == 11, "launch_detect_stream: fused softmax needs 11 classes (got %d)", C);
   const size_t rows = (size_t)batch * C;
   const int cap = stream_cap(top_k);
   unsigned char* p = reinterpret_cast<unsigned char*>(ws);
@@ -885,11 +912,13 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     const dim3 grid(chunks, batch);
     const size_t tile_bytes = kScanStages * sizeof(float) * kScanBlock * 11;
     const size_t smem0 = tile_bytes + sizeof(ScanShared<0, 11>), smem1 = tile_bytes + sizeof(ScanShared<1, 11>);
-    ROD_CUDA(cudaFuncSetAttribute(scan_kernel<0, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-    ROD_CUDA(cudaFuncSetAttribute(scan_kernel<1, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    scan_kernel<0, 11><<<grid, kScanBlock, smem0, st>>>(SP);
+    auto k0 = logits ? scan_kernel<0, 11, true> : scan_kernel<0, 11, false>;
+    auto k1 = logits ? scan_kernel<1, 11, true> : scan_kernel<1, 11, false>;
+    ROD_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+    ROD_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    k0<<<grid, kScanBlock, smem0, st>>>(SP);
     ROD_LAUNCH_CHECK("scan_kernel<0>");
-    scan_kernel<1, 11><<<grid, kScanBlock, smem1, st>>>(SP);
+    k1<<<grid, kScanBlock, smem1, st>>>(SP);
     ROD_LAUNCH_CHECK("scan_kernel<1>");
   } else {
     // ---- generic prediction depth: plain-load two-pass kernels, every segment takes the dense route

@@ -219,7 +219,7 @@ int launch_topk_selected(const SelectedScores& src, long long rows, int k, float
                          cudaStream_t st);
 size_t stream_workspace_bytes(int batch, int n_classes, int top_k);
 int launch_detect_stream(const Layout& L, const float* anchors_center, const LayeredF& probs, const LayeredF* loc,
-                         const LayeredF* refine, const LayeredF* det, int batch, int C, int ignore_class,
+                         const LayeredF* refine, const LayeredF* det, int batch, int C, int logits, int ignore_class,
                          float select_thr, float nms_thr, int top_k, int keep, const float* clip, float* out_scores,
                          float* out_boxes, int32_t* out_counts, void* ws, const unsigned** cnt_out, int* cap_out,
                          cudaStream_t st);
@@ -258,14 +258,14 @@ extern "C" size_t rod_detect_workspace_bytes(const rod_layout_t* layout, int bat
   return ((per * 4 + 255) / 256) * 256 * 2 + 256 + rod::stream_workspace_bytes(batch, n_classes, top_k);
 }
 
-extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_center,
+namespace rod {
+static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
                           const rod_layered_t* predictions, const rod_layered_t* localizations,
                           const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
                           int n_classes, int ignore_class, float select_threshold, float nms_threshold,
                           int top_k, int keep_top_k, const float* clip_box, float* out_scores,
                           float* out_bboxes, int32_t* out_counts, void* workspace, size_t workspace_bytes,
-                          void* stream) {
-  using namespace rod;
+                          void* stream, int logits) {
   int rc = check_layout(layout);
   if (rc) return rc;
   const int nl = layout->n_layers;
@@ -299,14 +299,15 @@ extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_cente
   const LayeredF probs_l = to_layered_f(predictions, nl);
   const unsigned* over_cnt = nullptr;
   int over_cap = 0;
-  if (select_threshold > 0.f) {
+  // (fused softmax is specialised for 11 classes; other depths take the general path below)
+  if (select_threshold > 0.f && (!logits || n_classes == 11)) {
     const LayeredF loc_l = localizations ? to_layered_f(localizations, nl) : probs_l;
     const LayeredF ref_l = localizations ? probs_l : to_layered_f(refine_out, nl);
     const LayeredF det_l = localizations ? probs_l : to_layered_f(det_out, nl);
     void* ws_stream = reinterpret_cast<unsigned char*>(workspace) + 2 * per;
     if ((rc = launch_detect_stream(L, anchors_center, probs_l, localizations ? &loc_l : nullptr,
                                    localizations ? nullptr : &ref_l, localizations ? nullptr : &det_l, batch,
-                                   n_classes, ignore_class, select_threshold, nms_threshold, top_k, keep_top_k,
+                                   n_classes, logits, ignore_class, select_threshold, nms_threshold, top_k, keep_top_k,
                                    clip_box, out_scores, out_bboxes, out_counts, ws_stream, &over_cnt, &over_cap, st)))
       return rc;
   } else if (out_counts) {
@@ -320,6 +321,7 @@ extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_cente
   src.n_classes = n_classes;
   src.ignore_class = ignore_class;
   src.batch = batch;
+  src.logits = logits;
   src.thr = select_threshold;
   src.over_cnt = over_cnt;
   src.over_cap = (unsigned)over_cap;
@@ -347,4 +349,29 @@ extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_cente
                                             out_scores, out_bboxes, nullptr, out_counts);
   ROD_LAUNCH_CHECK("nms_kernel<fused>");
   return ROD_OK;
+}
+}  // namespace rod
+
+extern "C" int rod_detect(const rod_layout_t* layout, const float* anchors_center,
+                          const rod_layered_t* predictions, const rod_layered_t* localizations,
+                          const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
+                          int n_classes, int ignore_class, float select_threshold, float nms_threshold,
+                          int top_k, int keep_top_k, const float* clip_box, float* out_scores,
+                          float* out_bboxes, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  return rod::detect_impl(layout, anchors_center, predictions, localizations, refine_out, det_out, batch, n_classes,
+                          ignore_class, select_threshold, nms_threshold, top_k, keep_top_k, clip_box, out_scores,
+                          out_bboxes, out_counts, workspace, workspace_bytes, stream, 0);
+}
+
+extern "C" int rod_detect_logits(const rod_layout_t* layout, const float* anchors_center,
+                                 const rod_layered_t* logits, const rod_layered_t* localizations,
+                                 const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
+                                 int n_classes, int ignore_class, float select_threshold, float nms_threshold,
+                                 int top_k, int keep_top_k, const float* clip_box, float* out_scores,
+                                 float* out_bboxes, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  return rod::detect_impl(layout, anchors_center, logits, localizations, refine_out, det_out, batch, n_classes,
+                          ignore_class, select_threshold, nms_threshold, top_k, keep_top_k, clip_box, out_scores,
+                          out_bboxes, out_counts, workspace, workspace_bytes, stream, 1);
 }

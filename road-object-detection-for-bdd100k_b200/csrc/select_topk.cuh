@@ -23,6 +23,7 @@ struct SelectedScores {
   LayeredF probs;
   Layout L;
   int n_classes, ignore_class, batch;
+  int logits;                 // predictions are logits: softmax on the fly (same bits as the fused select)
   float thr;
   const unsigned* over_cnt;   // when set: only segments whose streaming list overflowed are active
   unsigned over_cap;
@@ -33,7 +34,8 @@ struct SelectedScores {
   __device__ __forceinline__ float fetch(long long r, int i, bool& real) const {
     const int c = (int)(r / batch), b = (int)(r % batch);
     const int l = layer_of(L, i);
-    const float p = __ldg(probs.base[l] + (long long)b * probs.stride[l] + (long long)(i - L.offset[l]) * n_classes + c);
+    const float* row = probs.base[l] + (long long)b * probs.stride[l] + (long long)(i - L.offset[l]) * n_classes;
+    const float p = logits ? softmax_pick(row, n_classes, c) : __ldg(row + c);
     real = p >= thr;
     return __fmul_rn(p, real ? 1.f : 0.f);
   }

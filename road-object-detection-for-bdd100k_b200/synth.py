@@ -51,11 +51,17 @@ def head_offsets(image_index: int, n_anchors: int, salt: int = 0, sigma_c=0.1, s
     return o
 
 
-def class_probs(image_index: int, n_anchors: int, n_cols: int = 11):
-    """Post-softmax scores [N,11] f32: logits 3*N(0,1) with +4 on background."""
+def class_logits(image_index: int, n_anchors: int, n_cols: int = 11):
+    """Class logits [N,11] f32 behind class_probs: 3*N(0,1) with +4 on background."""
     rng = np.random.default_rng([BASE_SEED + int(image_index), 104729])
     z = (rng.standard_normal(size=(n_anchors, n_cols)) * 3.0).astype(np.float32)
     z[:, 0] += np.float32(4.0)
+    return z
+
+
+def class_probs(image_index: int, n_anchors: int, n_cols: int = 11):
+    """Post-softmax scores [N,11] f32: logits 3*N(0,1) with +4 on background."""
+    z = class_logits(image_index, n_anchors, n_cols)
     z -= z.max(axis=1, keepdims=True)
     e = np.exp(z)
     return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)

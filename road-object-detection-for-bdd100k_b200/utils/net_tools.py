@@ -328,7 +328,7 @@ def _select(preds, locs, select_threshold, num_classes, ignore_class):
 
 # --------------------------------------------------------------------------------- a15 post-process
 def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_threshold, clipping_bbox,
-            top_k, keep_top_k, num_classes, return_counts):
+            top_k, keep_top_k, num_classes, return_counts, from_logits=False):
     thr = 0.0 if select_threshold is None else float(select_threshold)
     preds = [_f32(p, "predictions") for p in preds]
     dev, B, C = preds[0].device, preds[0].shape[0], preds[0].shape[-1]
@@ -353,7 +353,8 @@ def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_thr
             clip = torch.as_tensor(clipping_bbox, dtype=torch.float32, device=dev).reshape(4).contiguous()
         a = _abi.DLArgs()
         with _abi.device_guard(dev):
-            _abi.check(_abi.lib.rod_dl_detect(
+            entry = _abi.lib.rod_dl_detect_logits if from_logits else _abi.lib.rod_dl_detect
+            _abi.check(entry(
                 lay, a.one(center), a.many(preds), a.many(locs), a.many(refine_out), a.many(det_out), 0, thr,
                 float(nms_threshold), int(top_k), int(keep_top_k), a.one(clip), a.one(scores), a.one(boxes),
                 a.one(counts), a.one(ws), _abi.stream_ptr(dev)))
@@ -364,24 +365,41 @@ def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_thr
     return rscores, rbboxes
 
 
+def softmax(clf_out, out=None):
+    """slim.softmax over the class axis for one tensor or a per-layer list (evaluate.py:136-137,
+    predict.py:127-128).  `out` may alias the input.  Same arithmetic as the softmax fused into
+    detected_bboxes(..., from_logits=True), so both routes give identical detections."""
+    if isinstance(clf_out, (list, tuple)):
+        outs = out if out is not None else [None] * len(clf_out)
+        return [softmax(t, o) for t, o in zip(clf_out, outs)]
+    x = _f32(clf_out, "clf_out").contiguous()
+    y = torch.empty_like(x) if out is None else out
+    if x.numel():
+        a = _abi.DLArgs()
+        with _abi.device_guard(x.device):
+            _abi.check(_abi.lib.rod_dl_softmax(a.one(x), a.one(y), _abi.stream_ptr(x.device)))
+    return y
+
+
 def detected_bboxes(predictions, localisations, select_threshold=None, nms_threshold=0.5,
-                    clipping_bbox=None, top_k=800, keep_top_k=200, return_counts=False):
+                    clipping_bbox=None, top_k=800, keep_top_k=200, return_counts=False, from_logits=False):
     """select -> top_k -> per-class NMS -> zero-pad (-> clip) in two kernels
-    (utils/net_tools.py:739-758).  predictions: list of [B,fh,fw,A,11] post-softmax scores;
+    (utils/net_tools.py:739-758).  predictions: list of [B,fh,fw,A,11] post-softmax scores (or the
+    class logits with from_logits=True: slim.softmax is then fused into the select pass);
     localisations: list of [B,fh,fw,A,4] corner boxes.  Returns dicts c -> [B,keep_top_k],
     c -> [B,keep_top_k,4] for c = 1..config.total_obj_n-1."""
     locs = [_f32(l, "localisations") for l in localisations]
     return _detect(list(predictions), locs, None, None, None, select_threshold, nms_threshold,
-                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts)
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits)
 
 
 def decode_detected_bboxes(anchors_all_layer, refine_out, det_out, predictions, select_threshold=None,
                            nms_threshold=0.5, clipping_bbox=None, top_k=800, keep_top_k=200,
-                           return_counts=False):
+                           return_counts=False, from_logits=False):
     """Extension: the inference call sequence of evaluate.py:139-151 in one call —
     c2c(decode(anchors, refine_out + det_out)) is evaluated only for the top_k candidates of
     each (image, class) instead of materialising [B,N,4] boxes first."""
     ro = [_f32(t, "refine_out") for t in refine_out]
     do = [_f32(t, "det_out") for t in det_out]
     return _detect(list(predictions), None, ro, do, anchors_all_layer, select_threshold, nms_threshold,
-                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts)
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits)
