@@ -466,6 +466,9 @@ def main():
         for name, stress in (("decode_nms", False), ("nms_stress", True)):
             line[name] = bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_loop, hbm_gbs, N)
 
+        if world == 1:
+            line["decode_nms_from_logits"] = bench_detect_logits(args, dev, table, to_dev_list, time_loop, hbm_gbs, N)
+
     if rank == 0 and not args.skip_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline("match_encode", args.cpu_seconds)
         if not args.skip_secondary:
@@ -593,6 +596,62 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
                   "h2d_bytes_per_step": sum(x.numel() * 4 for x in h_p + h_ro + h_do),
                   "d2h_bytes_per_step": (h_s[1:].numel() + h_b[1:].numel()) * 4,
                   "api": "net_tools.decode_detected_bboxes on pinned host inputs; scores+boxes read back; two batches in flight"}
+    return res
+
+
+def bench_detect_logits(args, dev, table, to_dev_list, time_loop, hbm_gbs, N):
+    """the decode_nms workload fed with class LOGITS.  Fused = softmax inside the select
+    pass (no probability tensor in HBM); unfused = net_tools.softmax (writes [B,N,11]) + the same detect."""
+    import torch
+    from rodet_b200 import synth
+    from rodet_b200.utils import net_tools
+    B = args.batch_detect
+    n_sets = max(2, args.streams)
+    sets = []
+    for s in range(n_sets):
+        first = 700_000 + s * B
+        z = np.stack([synth.class_logits(first + b, N_ANCHORS) for b in range(B)])
+        ro = np.stack([synth.head_offsets(first + b, N_ANCHORS, 0, 0.1, 0.2) for b in range(B)])
+        do = np.stack([synth.head_offsets(first + b, N_ANCHORS, 1, 0.1, 0.2) for b in range(B)])
+        d = {"z": to_dev_list(z, (N_CLASSES,)), "ro": to_dev_list(ro, (4,)), "do": to_dev_list(do, (4,))}
+        d["p"] = [torch.empty_like(t) for t in d["z"]]
+        sets.append(d)
+    kw = dict(select_threshold=SELECT_THR, nms_threshold=NMS_THR, top_k=TOP_K, keep_top_k=KEEP, return_counts=True)
+
+    def fused(s):
+        return net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["z"], from_logits=True, **kw)
+
+    def unfused(s):
+        net_tools.softmax(s["z"], out=s["p"])
+        return net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["p"], **kw)
+
+    res = {}
+    steps = max(10, args.steps // 4)
+    ns = 1 if args.no_graphs else args.streams
+    for name, fn in (("fused", fused), ("softmax_then_detect", unfused)):
+        for s in sets:
+            s["out_" + name] = fn(s)
+        torch.cuda.synchronize(dev)
+        if not args.no_graphs:
+            for s in sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    s["gout_" + name] = fn(s)
+                s["graph_" + name] = g
+        step = (lambda i, name=name: sets[i % n_sets]["graph_" + name].replay()) if not args.no_graphs else \
+               (lambda i, fn=fn: fn(sets[i % n_sets]))
+        ms = time_loop(step, steps, 2 * n_sets, ns)
+        res["ms_per_step_" + name] = ms / steps
+    same = all(torch.equal(s["out_fused"][0][c], s["out_softmax_then_detect"][0][c]) for s in sets for c in range(1, N_CLASSES))
+    alg_bytes = B * (76 * N + (N_CLASSES - 1) * KEEP * 20)
+    ms = res["ms_per_step_fused"]
+    res.update({"metric": "images/sec (softmax+decode+NMS)", "value": B / (ms * 1e-3), "unit": "images/s", "streams": ns,
+                "batch_per_gpu": B, "fused_equals_unfused": bool(same),
+                "config": {"workload": "decode_nms fed with class logits (SURVEY.md section 8 f-1): softmax fused into the select pass"},
+                "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                             "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes_per_step": alg_bytes},
+                "gpu_launches": 5 * steps,
+                "detections_per_image": float(sets[0]["out_fused"][2].sum().item()) / B})
     return res
 
 
