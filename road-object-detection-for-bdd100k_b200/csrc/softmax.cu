@@ -7,22 +7,23 @@ namespace rod {
 
 constexpr int kSoftmaxBlock = 256;
 
-// 256 rows per tile: coalesced load into shared memory (row stride C | 1: conflict-free), one thread
-// per row, coalesced store.  HBM-bound: 8 * C bytes per row.
+// 256 rows per tile: the tile's 256 * C floats are copied linearly into shared memory (float4 when the
+// tensor is 16 B aligned), one thread per row works on its C words in place (stride C: conflict-free
+// for odd C), and the tile is copied back linearly.  HBM-bound: 8 * C bytes per row.
 __global__ void __launch_bounds__(kSoftmaxBlock)
-softmax_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C) {
-  extern __shared__ float s_x[];
-  const int stride = C | 1, tid = threadIdx.x;
+softmax_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C, int vec) {
+  extern __shared__ __align__(16) float s_x[];
+  const int tid = threadIdx.x;
   for (long long r0 = (long long)blockIdx.x * kSoftmaxBlock; r0 < rows; r0 += (long long)gridDim.x * kSoftmaxBlock) {
     const int nrow = (int)(rows - r0 < kSoftmaxBlock ? rows - r0 : kSoftmaxBlock), total = nrow * C;
     const float* src = in + r0 * C;
-    for (int i = tid; i < total; i += kSoftmaxBlock) {
-      const int row = i / C;
-      s_x[row * stride + (i - row * C)] = __ldg(src + i);
-    }
+    float* dst = out + r0 * C;
+    const int nv = vec ? total >> 2 : 0;               // r0 * C is a multiple of 256 floats: tiles stay aligned
+    for (int i = tid; i < nv; i += kSoftmaxBlock) reinterpret_cast<float4*>(s_x)[i] = ldg4(src + 4 * i);
+    for (int i = 4 * nv + tid; i < total; i += kSoftmaxBlock) s_x[i] = __ldg(src + i);
     __syncthreads();
     if (tid < nrow) {
-      float* x = s_x + tid * stride;
+      float* x = s_x + tid * C;
       float m = x[0];
       for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
       float sum = 0.f;
@@ -35,11 +36,8 @@ softmax_kernel(const float* __restrict__ in, float* __restrict__ out, long long 
       for (int c = 0; c < C; ++c) x[c] = __fmul_rn(x[c], rinv);
     }
     __syncthreads();
-    float* dst = out + r0 * C;
-    for (int i = tid; i < total; i += kSoftmaxBlock) {
-      const int row = i / C;
-      __stcs(dst + i, s_x[row * stride + (i - row * C)]);
-    }
+    for (int i = tid; i < nv; i += kSoftmaxBlock) st4_cs(dst + 4 * i, reinterpret_cast<const float4*>(s_x)[i]);
+    for (int i = 4 * nv + tid; i < total; i += kSoftmaxBlock) __stcs(dst + i, s_x[i]);
     __syncthreads();
   }
 }
@@ -52,11 +50,12 @@ extern "C" int rod_softmax(const float* logits, int64_t rows, int n_classes, flo
   ROD_REQUIRE(rows >= 0 && n_classes >= 1 && n_classes <= ROD_MAX_CLASSES, "rod_softmax: rows=%lld n_classes=%d invalid",
               (long long)rows, n_classes);
   if (rows == 0) return ROD_OK;
-  const size_t smem = (size_t)kSoftmaxBlock * (n_classes | 1) * sizeof(float);
+  const size_t smem = (size_t)kSoftmaxBlock * n_classes * sizeof(float);
   ROD_CUDA(cudaFuncSetAttribute(softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (rows + kSoftmaxBlock - 1) / kSoftmaxBlock;
   const long long cap = 8ll * sm_count();
-  softmax_kernel<<<(unsigned)(tiles < cap ? tiles : cap), kSoftmaxBlock, smem, (cudaStream_t)stream>>>(logits, out, rows, n_classes);
+  softmax_kernel<<<(unsigned)(tiles < cap ? tiles : cap), kSoftmaxBlock, smem, (cudaStream_t)stream>>>(logits, out, rows, n_classes,
+      ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 ? 1 : 0);
   ROD_LAUNCH_CHECK("softmax_kernel");
   return ROD_OK;
 }
