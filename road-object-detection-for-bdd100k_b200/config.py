@@ -26,6 +26,12 @@ feat_size_512 = {'layer_1': (64, 64), 'layer_2': (32, 32), 'layer_3': (16, 16),
 
 
 @unique
+class train_range(Enum):               # config.py:52-55 (selects what the net factory returns)
+    REFINE = 0
+    ALL = 1
+
+
+@unique
 class refine_method(Enum):             # config.py:73-77
     NEAREST_NEIGHBOR = 0
     JACCARD_BIGGER = 1

@@ -174,3 +174,30 @@ def test_synth_is_deterministic_and_in_domain():
     assert np.allclose(p.sum(1), 1, atol=1e-5) and p.dtype == np.float32
     s = synth.stress_probs(3, 500)
     assert (s >= np.float32(0.3)).all()
+
+
+def test_catch_net_layout_helpers():
+    """nets/catch_net.py:306-308, 339-341, 344-363: head layout views and get_output's selection rule."""
+    import torch
+    from rodet_b200 import config
+    from rodet_b200.nets import catch_net
+    det_s, clf_s = catch_net.head_shapes(2)
+    assert det_s[0] == (2, 53, 53, 6, 4) and clf_s[5] == (2, 2, 2, 9, 11)
+    assert sum(s[1] * s[2] * s[3] for s in det_s) == 25800
+    det_c = [torch.arange(2 * fh * fw * a * 4, dtype=torch.float32).reshape(2, fh, fw, a * 4) for (_, fh, fw, a, _) in det_s]
+    clf_c = [torch.zeros(2, fh, fw, a * 11) for (_, fh, fw, a, _) in det_s]
+    net = catch_net.factory(det_c, det_c, clf_c, config_dict={'train_range': config.train_range.ALL})
+    ro, do, co = net.get_output()
+    assert [tuple(t.shape) for t in ro] == det_s and [tuple(t.shape) for t in co] == clf_s
+    assert ro[0].data_ptr() == det_c[0].data_ptr()                       # views, not copies
+    assert ro[1][1, 3, 4, 2, 1] == det_c[1][1, 3, 4, 2 * 4 + 1]          # channel = a * 4 + k
+    only = catch_net.factory(det_c, config_dict={'train_range': config.train_range.REFINE}).get_output()
+    assert len(only) == 6 and tuple(only[2].shape) == det_s[2]
+    with pytest.raises(ValueError):
+        catch_net.det_out(det_c[:3])
+    with pytest.raises(ValueError):
+        catch_net.clf_out(det_c)
+    bad = catch_net.factory(det_c, det_c, clf_c)
+    bad.train_range = None
+    with pytest.raises(ValueError, match='Error'):
+        bad.get_output()
