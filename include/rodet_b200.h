@@ -239,6 +239,32 @@ int rod_bboxes_matching_batch(int64_t label, const float* scores, const float* b
                               int n, int g_n, float matching_threshold, int64_t* out_n_gbboxes,
                               uint8_t* out_tp, uint8_t* out_fp, void* stream);
 
+/* ---- f-2  evaluation metrics (evaluate.py:162-197) ----------------------------------
+ * rod_tpfp_append replaces the update of tfe.streaming_tp_fp_arrays
+ * (utils/tf_extended/metrics.py:133-204) for `rows` classes at once: scores / tp / fp [rows, n]
+ * (n = batch * keep_top_k detections in image order); keeps, in order, the entries with tp | fp and
+ * score > rm_threshold (all entries when remove_zero_scores == 0, as the reference does) and appends
+ * them to v_scores / v_tp / v_fp [rows, capacity] at v_count[rows] (device counters, updated);
+ * v_ids (optional) receives id_base + position, a global detection id that makes merges across
+ * ranks order-independent; v_nobjects[rows] += sum(num_gbboxes[rows, n_gb]).  The caller guarantees
+ * capacity >= v_count + n (entries beyond capacity are dropped, the counter still advances).
+ * rod_precision_recall replaces tfe.precision_recall (:100-130) AFTER the descending score sort:
+ * float64 cumulative sums, recall = tp_c / num_gbboxes, precision = tp_c / (tp_c + fp_c), 0 where
+ * the denominator is <= 0.  num_gbboxes: device int64 scalar.
+ * rod_average_precision replaces tfe.average_precision_voc07 and _voc12 (:210-258):
+ * out[0] = VOC07 11-point AP (thresholds07 = the 11 recall levels np.arange(0., 1.1, 0.1), host),
+ * out[1] = VOC12 area AP, both float64 on the device. */
+int rod_tpfp_append(const float* scores, const uint8_t* tp, const uint8_t* fp, int rows, int64_t n,
+                    const int64_t* num_gbboxes, int n_gb, int remove_zero_scores, float rm_threshold,
+                    int64_t id_base, float* v_scores, uint8_t* v_tp, uint8_t* v_fp, int64_t* v_ids,
+                    int64_t capacity, int64_t* v_count, int64_t* v_nobjects, void* stream);
+size_t rod_precision_recall_workspace_bytes(int64_t n);
+int rod_precision_recall(const uint8_t* tp_sorted, const uint8_t* fp_sorted, int64_t n,
+                         const int64_t* num_gbboxes, double* precision, double* recall,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int rod_average_precision(const double* precision, const double* recall, int64_t n,
+                          const double* thresholds07, double* out_voc07_voc12, void* stream);
+
 /* ---- measurement helpers (bench.py) ------------------------------------------------
  * rod_peak_fp32_nofma: runs a dependent-chain FADD/FMUL (no FMA) kernel and returns in
  * *ops the number of FP32 instructions-lanes issued; time it with events on `stream`. */

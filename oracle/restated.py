@@ -511,3 +511,72 @@ def bboxes_matching_batch(labels, scores, bboxes, glabels, gbboxes, gdifficults,
            for i in range(len(scores))]
     return (np.asarray([o[0] for o in out], dtype=np.int64), np.stack([o[1] for o in out]),
             np.stack([o[2] for o in out]), scores)
+
+
+# --------------------------------------------------------------------------- #
+# f-2  evaluation metrics  (utils/tf_extended/metrics.py:100-258, evaluate.py:162-197)
+# --------------------------------------------------------------------------- #
+class StreamingTpFp:
+    """The local variables of tfe.streaming_tp_fp_arrays and its update op (metrics.py:157-195)."""
+
+    def __init__(self):
+        self.nobjects, self.ndetections = np.int64(0), np.int32(0)
+        self.scores = np.zeros((0,), f32)
+        self.tp = np.zeros((0,), bool)
+        self.fp = np.zeros((0,), bool)
+
+    def update(self, num_gbboxes, tp, fp, scores, remove_zero_scores=True):
+        scores = np.asarray(scores, dtype=f32).reshape(-1)
+        tp = np.asarray(tp).astype(bool).reshape(-1)
+        fp = np.asarray(fp).astype(bool).reshape(-1)
+        if remove_zero_scores:                                   # the mask is only applied in this branch (:164-170)
+            mask = (tp | fp) & (scores > f32(1e-4))
+            scores, tp, fp = scores[mask], tp[mask], fp[mask]
+        self.nobjects = np.int64(self.nobjects + np.asarray(num_gbboxes, dtype=np.int64).sum())
+        self.ndetections = np.int32(self.ndetections + scores.size)
+        self.scores = np.concatenate([self.scores, scores])
+        self.tp = np.concatenate([self.tp, tp])
+        self.fp = np.concatenate([self.fp, fp])
+        return self.value()
+
+    def value(self):
+        return self.nobjects, self.ndetections, self.tp, self.fp, self.scores
+
+
+def precision_recall(num_gbboxes, num_detections, tp, fp, scores):
+    """metrics.py:117-130: top_k sort (ties: lower index first), float64 cumsums, _safe_div."""
+    scores = np.asarray(scores, dtype=f32).reshape(-1)
+    k = int(num_detections)
+    idx = np.argsort(-scores, kind="stable")[:k]
+    tpc = np.cumsum(np.asarray(tp).reshape(-1)[idx].astype(np.float64))
+    fpc = np.cumsum(np.asarray(fp).reshape(-1)[idx].astype(np.float64))
+    ngb = np.float64(num_gbboxes)
+    with np.errstate(all="ignore"):
+        recall = np.where(ngb > 0, tpc / ngb, 0.0)
+        precision = np.where(tpc + fpc > 0, tpc / (tpc + fpc), 0.0)
+    return precision, recall
+
+
+def cummax(x, reverse=False):
+    """utils/tf_extended/math.py:41-67."""
+    x = np.asarray(x)
+    return np.maximum.accumulate(x[::-1])[::-1] if reverse else np.maximum.accumulate(x)
+
+
+def average_precision_voc12(precision, recall):
+    """metrics.py:210-232."""
+    p = np.concatenate([[0.], np.asarray(precision, np.float64), [0.]])
+    r = np.concatenate([[0.], np.asarray(recall, np.float64), [1.]])
+    p = cummax(p, reverse=True)
+    return np.float64(np.sum(p[1:] * (r[1:] - r[:-1])))
+
+
+def average_precision_voc07(precision, recall):
+    """metrics.py:235-258: 11 recall levels np.arange(0., 1.1, 0.1), each max / 11, summed in order."""
+    p = np.concatenate([np.asarray(precision, np.float64), [0.]])
+    r = np.concatenate([np.asarray(recall, np.float64), [np.inf]])
+    ap = None
+    for t in np.arange(0., 1.1, 0.1):
+        v = np.max(p[r >= t]) / 11.
+        ap = v if ap is None else ap + v
+    return np.float64(ap)

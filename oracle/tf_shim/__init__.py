@@ -360,6 +360,41 @@ def _build_tf_module():
                              mode="constant", constant_values=constant_values))
     tf.pad = pad
 
+    def cumsum(x, axis=0, exclusive=False, reverse=False, name=None):
+        assert not exclusive and not reverse
+        return Tensor(np.cumsum(_t(x).a, axis=axis, dtype=_t(x).a.dtype))
+    tf.cumsum = cumsum
+    tf.tuple = lambda tensors, name=None, control_inputs=None: [_t(t) for t in tensors]
+
+    def add_n(inputs, name=None):
+        acc = _t(inputs[0])
+        for v in inputs[1:]:
+            acc = acc + v                       # AddN accumulates its inputs in order
+        return acc
+    tf.add_n = add_n
+
+    def reverse(x, axis, name=None):
+        return Tensor(np.flip(_t(x).a, axis=tuple(int(a) for a in axis)))
+    tf.reverse = reverse
+
+    def scan(fn, elems, initializer=None, parallel_iterations=10, back_prop=True, swap_memory=False,
+             infer_shape=True, reverse=False, name=None):
+        a = _t(elems).a
+        assert not reverse
+        if a.shape[0] == 0:
+            return Tensor(a.copy())
+        out, acc, start = [], None, 0
+        if initializer is None:
+            acc, start = Tensor(a[0]), 1
+            out.append(acc.a)
+        else:
+            acc = _t(initializer)
+        for i in range(start, a.shape[0]):
+            acc = _t(fn(acc, Tensor(a[i])))
+            out.append(acc.a)
+        return Tensor(np.stack(out).astype(a.dtype))
+    tf.scan = scan
+
     def boolean_mask(x, mask, name=None, axis=None):
         return Tensor(_t(x).a[np.asarray(_unwrap(mask), dtype=bool)])
     tf.boolean_mask = boolean_mask
@@ -548,7 +583,20 @@ def install():
     math_ops.mul = tf.multiply
     math_ops.to_float = lambda x, name=None: tf.cast(x, np.float32)
     math_ops.to_int64 = lambda x, name=None: tf.cast(x, np.int64)
+    # tensorflow.python.framework.ops is *executed* by tf_extended/math.py:cummax and metrics.py
+    import contextlib
+    fw_ops = types.ModuleType("tensorflow.python.framework.ops")
+    fw_ops.__path__ = []
+
+    @contextlib.contextmanager
+    def _ops_name_scope(name=None, default_name=None, values=None):
+        yield name or default_name
+    fw_ops.name_scope = _ops_name_scope
+    fw_ops.convert_to_tensor = lambda v, dtype=None, name=None: tf.convert_to_tensor(v, dtype=dtype)
+    fw_ops.GraphKeys = mock.MagicMock(name="GraphKeys")
+    fw_ops.add_to_collections = lambda *a, **k: None
     real = {
+        "tensorflow.python.framework.ops": fw_ops,
         "tensorflow": tf,
         "tensorflow.nn": tf.nn,
         "tensorflow.image": tf.image,

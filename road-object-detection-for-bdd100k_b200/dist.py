@@ -61,3 +61,38 @@ def allgather_counts(counts: torch.Tensor, n_images: int, group=None, async_op: 
         work = dist.all_gather(parts, mine, group=group, async_op=True)
         pending = PendingCounts(work, parts, sizes, False)
     return pending if async_op else pending.result()
+
+
+def allgather_tp_fp(value, group=None):
+    """The exchange step of a sharded evaluation: merges the per-rank arrays accumulated by
+    `tfe.streaming_tp_fp_arrays` (`StreamingTpFp.value(row, with_ids=True)` =
+    (num_gbboxes, num_detections, tp, fp, scores, ids)) into the arrays a single process would hold.
+    Lengths differ per rank: the counts are all-gathered first, the arrays are padded to the longest
+    and all-gathered (NCCL over NVLink on GPUs), then put back into global detection order by `ids`
+    (ties between equal scores are broken by position in `precision_recall`, so order matters).
+    Returns (num_gbboxes, num_detections, tp, fp, scores) on every rank."""
+    nobj, ndet, tp, fp, scores, ids = value
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        order = torch.argsort(ids, stable=True)
+        return nobj, ndet, tp[order], fp[order], scores[order]
+    world = dist.get_world_size(group)
+    dev = scores.device
+    n_local = torch.tensor([scores.numel(), int(nobj)], dtype=torch.int64, device=dev)
+    sizes = [torch.empty_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    counts = [int(s[0]) for s in sizes]
+    width = max(counts)
+    # one padded [3, width] int64 block per rank: score bits, tp | fp << 1, ids
+    mine = torch.zeros((3, width), dtype=torch.int64, device=dev)
+    n = scores.numel()
+    mine[0, :n] = scores.contiguous().view(torch.int32).to(torch.int64)
+    mine[1, :n] = tp.to(torch.int64) | (fp.to(torch.int64) << 1)
+    mine[2, :n] = ids
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    cat = torch.cat([p[:, :c] for p, c in zip(parts, counts)], dim=1)
+    order = torch.argsort(cat[2], stable=True)
+    cat = cat[:, order]
+    total_obj = sum(int(s[1]) for s in sizes)
+    return (torch.tensor(total_obj, dtype=torch.int64, device=dev), torch.tensor(cat.shape[1], dtype=torch.int32, device=dev),
+            (cat[1] & 1).bool(), ((cat[1] >> 1) & 1).bool(), cat[0].to(torch.int32).view(torch.float32))

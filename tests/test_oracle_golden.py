@@ -203,3 +203,28 @@ def test_eval_matching_restatement():
         assert np.array_equal(n[c], z["n_c%d" % c])
         assert np.array_equal(tp[c], z["tp_c%d" % c]) and np.array_equal(fp[c], z["fp_c%d" % c])
     assert sum(int(z["tp_c%d" % c].sum()) for c in cl) >= 8
+
+
+def test_eval_metrics_restatement():
+    """oracle/restated precision_recall / AP / cummax against the unmodified reference
+    (utils/tf_extended/metrics.py:100-130, 210-258; math.py:41-67) run by oracle/gen_golden_metrics.py."""
+    z = golden("eval_metrics.npz")
+    for i in range(int(z["n_cases"])):
+        s, tp, fp, ngb = z["scores_%d" % i], z["tp_%d" % i], z["fp_%d" % i], int(z["ngb_%d" % i])
+        p, r = R.precision_recall(ngb, s.size, tp, fp, s)
+        assert p.dtype == np.float64 and np.array_equal(p, z["precision_%d" % i]) and np.array_equal(r, z["recall_%d" % i])
+        assert R.average_precision_voc07(p, r) == z["voc07_%d" % i]
+        assert abs(R.average_precision_voc12(p, r) - z["voc12_%d" % i]) <= 1e-12 * max(1.0, abs(z["voc12_%d" % i]))
+    assert np.array_equal(R.cummax(z["cummax_in"]), z["cummax_fwd"])
+    assert np.array_equal(R.cummax(z["cummax_in"], reverse=True), z["cummax_rev"])
+    # streaming accumulation: filter (tp | fp) & score > 1e-4 only when remove_zero_scores
+    st = R.StreamingTpFp()
+    sc = np.asarray([[0.9, 0.5, 0.0], [0.00005, 0.3, 0.2]], np.float32)
+    tp = np.asarray([[1, 0, 0], [1, 0, 1]], bool)
+    fp = np.asarray([[0, 1, 0], [0, 0, 0]], bool)
+    st.update(np.asarray([2, 1]), tp, fp, sc)
+    no, nd, t, f, s = st.value()
+    assert int(no) == 3 and int(nd) == 3 and s.tolist() == [np.float32(0.9), np.float32(0.5), np.float32(0.2)]
+    assert t.tolist() == [True, False, True] and f.tolist() == [False, True, False]
+    st.update(np.asarray([4]), tp, fp, sc, remove_zero_scores=False)
+    assert int(st.value()[0]) == 7 and int(st.value()[1]) == 9 and st.value()[4].size == 9
