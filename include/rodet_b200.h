@@ -265,6 +265,22 @@ int rod_precision_recall(const uint8_t* tp_sorted, const uint8_t* fp_sorted, int
 int rod_average_precision(const double* precision, const double* recall, int64_t n,
                           const double* thresholds07, double* out_voc07_voc12, void* stream);
 
+/* ---- f-4  ground-truth boxes of the training input pipeline -------------------------
+ * The box half of process_raw_data_train (utils/data_pileline_tools.py:88-108), the step right
+ * before refine_groundtruth, fused and batched: per image b
+ *   bboxes = tfe.bboxes_resize(distort_bbox[b], bboxes)           (bboxes.py:139-163; skipped if NULL)
+ *   labels, bboxes = tfe.bboxes_filter_overlap(labels, bboxes, threshold, assign_negative)
+ *                                                                 (bboxes.py:408-428; if filter_overlap)
+ *   bboxes = flip_bboxes(bboxes) where mirror[b] != 0             (tf_image.py:284-289; skipped if NULL)
+ *   bboxes = min(max(bboxes, 0), 1)                               (data_pileline_tools.py:107-108; if clamp01)
+ * bboxes [batch,gmax,4] corner form, labels [batch,gmax] (int64 if labels_i64 else int32),
+ * counts[batch] valid boxes per image (NULL = gmax).  Kept boxes stay in order, the rest of each
+ * row is zeroed, out_counts[batch] receives the new counts. */
+int rod_gt_boxes_update(const float* bboxes, const void* labels, int labels_i64, const int32_t* counts,
+                        int batch, int gmax, const float* distort_bbox, const uint8_t* mirror,
+                        int filter_overlap, float threshold, int assign_negative, int clamp01,
+                        float* out_bboxes, void* out_labels, int32_t* out_counts, void* stream);
+
 /* ---- measurement helpers (bench.py) ------------------------------------------------
  * rod_peak_fp32_nofma: runs a dependent-chain FADD/FMUL (no FMA) kernel and returns in
  * *ops the number of FP32 instructions-lanes issued; time it with events on `stream`. */

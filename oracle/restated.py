@@ -580,3 +580,32 @@ def average_precision_voc07(precision, recall):
         v = np.max(p[r >= t]) / 11.
         ap = v if ap is None else ap + v
     return np.float64(ap)
+
+
+# --------------------------------------------------------------------------- #
+# f-4  ground-truth boxes of the training input pipeline
+# (utils/data_pileline_tools.py:88-108, process.py:134-138, tf_image.py:284-289)
+# --------------------------------------------------------------------------- #
+def bboxes_filter_overlap(labels, bboxes, threshold=0.5, assign_negative=False):
+    """utils/tf_extended/bboxes.py:408-428."""
+    labels = np.asarray(labels)
+    bboxes = np.asarray(bboxes, dtype=f32).reshape(-1, 4)
+    scores = bboxes_intersection(np.asarray([0, 0, 1, 1], f32), bboxes)
+    mask = scores > f32(threshold)
+    if assign_negative:
+        return np.where(mask, labels, -labels), bboxes
+    return labels[mask], bboxes[mask]
+
+
+def gt_boxes_train(labels, bboxes, distort_bbox=None, mirror=False, crop_overlap=0.3, assign_negative=False):
+    """One image: resize to the crop, drop boxes mostly outside it, flip, clamp to [0,1]."""
+    labels = np.asarray(labels)
+    b = np.asarray(bboxes, dtype=f32).reshape(-1, 4)
+    if distort_bbox is not None:
+        b = bboxes_resize(np.asarray(distort_bbox, f32), b)
+    if crop_overlap is not None:
+        labels, b = bboxes_filter_overlap(labels, b, crop_overlap, assign_negative)
+    if mirror:
+        b = np.stack([b[:, 0], f32(1) - b[:, 3], b[:, 2], f32(1) - b[:, 1]], axis=-1)       # tf_image.py:286-288
+    b = np.minimum(np.maximum(b, f32(0.)), f32(1.))                                        # data_pileline_tools.py:107-108
+    return labels, b.astype(f32)

@@ -72,6 +72,7 @@ SIGNATURES = {
     "rod_precision_recall_workspace_bytes": (_sz, [_i64]),
     "rod_precision_recall": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_average_precision": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "rod_gt_boxes_update": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)       # AttributeError here = header and library out of sync

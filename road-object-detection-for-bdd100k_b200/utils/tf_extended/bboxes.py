@@ -12,7 +12,7 @@ from ... import _abi
 
 __all__ = ["bboxes_sort_all_classes", "bboxes_sort", "bboxes_clip", "bboxes_resize", "bboxes_nms",
            "bboxes_nms_batch", "bboxes_jaccard", "bboxes_intersection", "bboxes_matching",
-           "bboxes_matching_batch"]
+           "bboxes_matching_batch", "bboxes_filter_overlap"]
 
 
 def _f32(t, name):
@@ -182,3 +182,38 @@ def bboxes_matching_batch(labels, scores, bboxes, glabels, gbboxes, gdifficults,
         return d_n_gbboxes, d_tp, d_fp, scores
     n, tp, fp = _matching(labels, scores, bboxes, glabels, gbboxes, gdifficults, matching_threshold)
     return n, tp, fp, scores
+
+
+def _gt_update(labels, bboxes, counts, distort_bbox, mirror, filter_overlap, threshold, assign_negative, clamp01):
+    b = _f32(bboxes, "bboxes").contiguous()
+    if b.dim() != 3 or b.shape[-1] != 4:
+        raise ValueError("bboxes must be [B,G,4]")
+    B, G = b.shape[0], b.shape[1]
+    lab = labels.contiguous()
+    if lab.dtype not in (torch.int64, torch.int32) or tuple(lab.shape) != (B, G) or lab.device != b.device:
+        raise ValueError("labels must be an int64 / int32 [B,G] tensor on the boxes' device")
+    dev = b.device
+    cnt = None if counts is None else counts.to(device=dev, dtype=torch.int32).contiguous()
+    crop = None if distort_bbox is None else torch.as_tensor(distort_bbox, dtype=torch.float32, device=dev).reshape(B, 4).contiguous()
+    mir = None if mirror is None else torch.as_tensor(mirror, device=dev).reshape(B).to(torch.uint8).contiguous()
+    ob, ol = torch.empty_like(b), torch.empty_like(lab)
+    oc = torch.empty(B, dtype=torch.int32, device=dev)
+    P = lambda t: None if t is None else t.data_ptr()
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib.rod_gt_boxes_update(b.data_ptr(), lab.data_ptr(), 1 if lab.dtype == torch.int64 else 0, P(cnt), B, G,
+                                                P(crop), P(mir), 1 if filter_overlap else 0, float(threshold),
+                                                1 if assign_negative else 0, 1 if clamp01 else 0, ob.data_ptr(), ol.data_ptr(),
+                                                oc.data_ptr(), _abi.stream_ptr(dev)))
+    return ol, ob, oc
+
+
+def bboxes_filter_overlap(labels, bboxes, threshold=0.5, assign_negative=False, scope=None):
+    """Drops (or, with assign_negative, negates the label of) the boxes whose overlap with [0,0,1,1],
+    relative to their own area, is not above `threshold` (utils/tf_extended/bboxes.py:408-428).
+    labels [G], bboxes [G,4] -> filtered labels, bboxes (the kept count is read back, like
+    tf.boolean_mask's dynamic shape)."""
+    ol, ob, oc = _gt_update(labels.unsqueeze(0), bboxes.unsqueeze(0), None, None, None, True, threshold, assign_negative, False)
+    if assign_negative:
+        return ol[0], ob[0]
+    k = int(oc[0].item())
+    return ol[0, :k], ob[0, :k]

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import LAYOUTS, golden, golden_anchors, golden_files
+from helpers import bit_equal
 from oracle import restated as R
 
 RTOL, ATOL = 1e-5, 1e-6
@@ -228,3 +229,15 @@ def test_eval_metrics_restatement():
     assert t.tolist() == [True, False, True] and f.tolist() == [False, True, False]
     st.update(np.asarray([4]), tp, fp, sc, remove_zero_scores=False)
     assert int(st.value()[0]) == 7 and int(st.value()[1]) == 9 and st.value()[4].size == 9
+
+
+def test_gt_boxes_pipeline_restatement():
+    """oracle/restated.gt_boxes_train against the unmodified tfe.bboxes_resize + bboxes_filter_overlap
+    (+ the flip / clamp lines) run by oracle/gen_golden_gtboxes.py."""
+    z = golden("gt_boxes.npz")
+    for b in range(int(z["B"])):
+        n = int(z["counts"][b])
+        for neg in (0, 1):
+            lab, bx = R.gt_boxes_train(z["labels"][b, :n], z["boxes"][b, :n], z["crops"][b], bool(z["mirror"][b]), 0.3, bool(neg))
+            assert np.array_equal(lab, z["labels_%d_%d" % (b, neg)]), (b, neg)
+            assert bit_equal(bx.reshape(-1, 4), z["bboxes_%d_%d" % (b, neg)]), (b, neg)
