@@ -5,22 +5,24 @@
 // With thr > 0 every entry the select stage zeroes (score*0, box*0) ranks below every real
 // candidate and is indistinguishable from pad_axis's zero padding in the output, so only the
 // candidates with p >= thr matter.  Per (class, image) segment:
-//   A1  scan_kernel<0>  ONE pass over the [B,N,C] scores.  256-anchor tiles are staged into shared
+//   A1  scan_kernel<0>  ONE pass over the [B,N,C] scores (or logits: <.,.,true> computes the softmax of
+//                       each anchor in registers first, f-1).  256-anchor tiles are staged into shared
 //                       memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered); one
-//                       thread per anchor.  Candidates (p >= thr) are counted in a per-segment
-//                       1024-bin histogram (packed 16-bit shared-memory counters, flushed once per
-//                       CTA) and, while they are sparse, appended to the segment's candidate list
-//                       (warp-aggregated, staged per tile).  A segment whose candidates are not sparse
-//                       (> 64 per class per tile, or > 4096 in total) is flagged "dense".
-//   T   thresh_kernel   suffix scan of the histogram -> the lowest bin still inside the top_k.
-//   A2  scan_kernel<1>  only for dense segments: second pass that appends the candidates at or
-//                       above the threshold bin (the NMS-stress workload takes this route).
-//   B   segment_kernel  one CTA per segment: filter the list by the threshold bin, bitonic sort
-//                       (score desc, anchor asc = tf.nn.top_k order), keep the first top_k, gather +
-//                       decode their boxes, batched greedy NMS, write keep_top_k rows zero padded.
+//                       thread per anchor.  Candidates (p >= thr) are counted in a per-segment 1024-bin
+//                       histogram (packed 16-bit shared-memory counters, flushed once per CTA) and
+//                       appended to this CTA's private slice of the segment's candidate list while the
+//                       slice has room.  A segment with a full slice is flagged "dense".
+//   A2  scan_kernel<1>  only for dense segments: second pass that appends the candidates at or above
+//                       the threshold bin, which it derives from the finished histogram itself (the
+//                       NMS-stress workload takes this route).
+//   B   segment_kernel  one CTA per segment: threshold bin from the histogram, filter the list, counting
+//                       sort on the score bins + exact in-bin rank (score desc, anchor asc = tf.nn.top_k
+//                       order), keep the first top_k, gather + decode their boxes, greedy NMS in batches
+//                       against the kept list, write keep_top_k rows zero padded.
 // A list that overflows the sort capacity (massive score ties at the threshold bin) is left to the
 // exact general kernels (topk_segment_kernel + nms_kernel), which re-run only for flagged segments.
-// Prediction depths other than 11 use the plain-load two-pass kernels (hist_kernel, collect_kernel).
+// Prediction depths other than 11 use the plain-load two-pass kernels (hist_kernel, thresh_kernel,
+// collect_kernel) in front of the same segment kernel.
 #include "select_topk.cuh"
 
 namespace rod {
