@@ -201,3 +201,14 @@ def test_catch_net_layout_helpers():
     bad.train_range = None
     with pytest.raises(ValueError, match='Error'):
         bad.get_output()
+
+
+def test_reshape_list_round_trip():
+    """utils/tf_extended/tf_utils.py:29-55 as used by train.py:114-124."""
+    from rodet_b200.utils.tf_extended import tf_utils
+    img, a, b = "img", ["a%d" % i for i in range(6)], ("b%d" % i for i in range(6))
+    b = list(b)
+    flat = tf_utils.reshape_list([img, a, tuple(b)])
+    assert flat == [img] + a + b
+    assert tf_utils.reshape_list(flat, [1, 6, 6]) == [img, a, b]
+    assert tf_utils.reshape_list([], None) == [] and tf_utils.reshape_list([1, 2], [1, 1]) == [1, 2]
