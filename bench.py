@@ -469,6 +469,7 @@ def main():
 
         if world == 1:
             line["decode_nms_from_logits"] = bench_detect_logits(args, dev, table, to_dev_list, time_loop, hbm_gbs, N)
+            line["targets_and_losses"] = bench_losses(args, dev, table, sets, arm, odm, to_dev_list, time_loop, hbm_gbs, N)
 
     if rank == 0 and not args.skip_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline("match_encode", args.cpu_seconds)
@@ -604,6 +605,56 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
                   "h2d_bytes_per_step": sum(x.numel() * 4 for x in h_p + h_ro + h_do),
                   "d2h_bytes_per_step": (h_s[1:].numel() + h_b[1:].numel()) * 4,
                   "api": "net_tools.decode_detected_bboxes on pinned host inputs; scores+boxes read back; two batches in flight"}
+    return res
+
+
+def bench_losses(args, dev, table, sets, arm, odm, to_dev_list, time_loop, hbm_gbs, N):
+    """the training epilogue ARM + ODM targets -> refine_loss + det_clf_loss (forward), and the
+    same with backward() to the head outputs, on the match_encode batch (B = 32)."""
+    import torch
+    from rodet_b200 import synth
+    from rodet_b200.utils import net_tools
+    B = args.batch
+    s = sets[0]
+    first = 800_000
+    s["do"] = to_dev_list(np.stack([synth.head_offsets(first + b, N_ANCHORS, 1) for b in range(B)]), (4,))
+    s["clf"] = to_dev_list(np.stack([synth.class_logits(first + b, N_ANCHORS) for b in range(B)]), (N_CLASSES,))
+
+    def forward(ro, do, clf):
+        t = arm(s)
+        d = net_tools.det_groundtruth(ro, t[0], t[1], t[2], t[3], table)
+        rl = net_tools.refine_loss(ro, t[0], t[3])
+        dl, cl = net_tools.det_clf_loss(ro, clf, do, d[0], d[1], d[2], d[3])
+        return rl + dl + cl
+
+    def step_fwd(i):
+        with torch.no_grad():
+            s["loss"] = forward(s["ro"], s["do"], s["clf"])
+
+    leaves = [[t.clone().requires_grad_(True) for t in s[k]] for k in ("ro", "do", "clf")]
+
+    def step_bwd(i):
+        for ts in leaves:
+            for t in ts:
+                t.grad = None
+        forward(*leaves).backward()
+
+    steps = max(10, args.steps // 8)
+    res = {"config": {"workload": "ARM + ODM targets + refine_loss + det_clf_loss (hard-negative mining), B = %d; "
+                                  "forward / forward_backward are eager launches through autograd, forward_graph is a CUDA-graph replay" % B}}
+    variants = [("forward", step_fwd), ("forward_backward", step_bwd)]
+    if not args.no_graphs:
+        step_fwd(0)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            s["gloss"] = forward(s["ro"], s["do"], s["clf"])
+        variants.append(("forward_graph", lambda i: g.replay()))
+    for name, fn in variants:
+        ms = time_loop(fn, steps, 3, 1)
+        res["ms_per_step_" + name] = ms / steps
+    res.update({"metric": "images/sec (targets + losses, forward)", "value": B / (res["ms_per_step_forward"] * 1e-3), "unit": "images/s",
+                "loss": float(s["loss"]), "batch_per_gpu": B})
     return res
 
 

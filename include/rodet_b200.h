@@ -265,6 +265,27 @@ int rod_precision_recall(const uint8_t* tp_sorted, const uint8_t* fp_sorted, int
 int rod_average_precision(const double* precision, const double* recall, int64_t n,
                           const double* thresholds07, double* out_voc07_voc12, void* stream);
 
+/* ---- f-3  losses on the ARM / ODM targets (utils/net_tools.py:478-623) ---------------
+ * rod_smooth_l1_loss: out_loss[0] = sum_{b,n,k} smooth_l1((y - x) * mask) / batch over all layers
+ * (smooth_l1 :478-489; refine_loss :492-516; det_loss :538-551).  y, x: per-layer [B,..,4] f32,
+ * mask: per-layer [B,..,1] i32.  grad_x (optional, flat [B,N,4]) receives d(loss * batch * grad_scale)/dx.
+ * rod_clf_loss: classification loss of det_clf_loss (:553-615).  logits per-layer [B,..,C] f32, labels and
+ * mask per-layer [B,..,1] i32 (det_labels, det_pos_mask), iou per-layer [B,..] f32 (iou_all_layers).
+ * out6 = {clf_loss, pos_loss, neg_loss, max_hard_pred, n_pos, n_neg} (device floats).  The workspace keeps
+ * what rod_clf_loss_grad needs: grad_logits (flat [B,N,C]) = upstream * d clf_loss / d logits, with masks,
+ * labels and the IoU factor treated as constants.  Tolerance parity (1e-5 relative). */
+size_t rod_smooth_l1_workspace_bytes(const rod_layout_t* layout, int batch);
+int rod_smooth_l1_loss(const rod_layout_t* layout, const rod_layered_t* y, const rod_layered_t* x,
+                       const rod_layered_t* mask, int batch, float* out_loss, float* grad_x,
+                       float grad_scale, void* workspace, size_t workspace_bytes, void* stream);
+size_t rod_clf_loss_workspace_bytes(const rod_layout_t* layout, int batch);
+int rod_clf_loss(const rod_layout_t* layout, const rod_layered_t* logits, const rod_layered_t* labels,
+                 const rod_layered_t* mask, const rod_layered_t* iou, int batch, int n_classes,
+                 float negative_ratio, float* out6, void* workspace, size_t workspace_bytes, void* stream);
+int rod_clf_loss_grad(const rod_layout_t* layout, const rod_layered_t* logits, const rod_layered_t* labels,
+                      const rod_layered_t* mask, const rod_layered_t* iou, int batch, int n_classes,
+                      float upstream, const void* workspace, float* grad_logits, void* stream);
+
 /* ---- f-4  ground-truth boxes of the training input pipeline -------------------------
  * The box half of process_raw_data_train (utils/data_pileline_tools.py:88-108), the step right
  * before refine_groundtruth, fused and batched: per image b

@@ -609,3 +609,65 @@ def gt_boxes_train(labels, bboxes, distort_bbox=None, mirror=False, crop_overlap
         b = np.stack([b[:, 0], f32(1) - b[:, 3], b[:, 2], f32(1) - b[:, 1]], axis=-1)       # tf_image.py:286-288
     b = np.minimum(np.maximum(b, f32(0.)), f32(1.))                                        # data_pileline_tools.py:107-108
     return labels, b.astype(f32)
+
+
+# --------------------------------------------------------------------------- #
+# f-3  losses  (utils/net_tools.py:478-623)
+# --------------------------------------------------------------------------- #
+def smooth_l1(x):
+    """:478-489."""
+    a = np.abs(x)
+    return 0.5 * ((a - 1) * np.minimum(a, 1) + a)
+
+
+def smooth_l1_loss(y_layers, x_layers, mask_layers):
+    """refine_loss (:492-516) / det_loss (:538-551): sum over layers of sum(smooth_l1((y - x) * mask)) / bs.
+    float32 element-wise ops as the reference, float64 accumulation."""
+    total = 0.0
+    bs = np.asarray(x_layers[0]).shape[0]
+    for y, x, m in zip(y_layers, x_layers, mask_layers):
+        y, x = np.asarray(y, f32), np.asarray(x, f32)
+        m = np.asarray(m).astype(f32).reshape(y.shape[:-1] + (1,))
+        total += float(np.sum(smooth_l1((y - x) * m).astype(np.float64))) / bs
+    return total
+
+
+def clf_loss(clf_layers, det_pos_mask, det_labels, iou_layers, negative_ratio=3.0):
+    """Classification half of det_clf_loss (:553-615).  Returns dict(clf_loss, pos_loss, neg_loss,
+    max_hard_pred, n_pos, n_neg, weights) — weights [B*N...] in the reference's flatten order are the
+    per-anchor cross-entropy weights (for the gradient check)."""
+    bs = np.asarray(clf_layers[0]).shape[0]
+    C = np.asarray(clf_layers[0]).shape[-1]
+    logits = np.concatenate([np.asarray(t, f32).reshape(-1, C) for t in clf_layers], axis=0)
+    gcls = np.concatenate([np.asarray(t).reshape(-1) for t in det_labels]).astype(np.int64)
+    pmask = np.concatenate([np.asarray(t).reshape(-1) for t in det_pos_mask]).astype(bool)
+    n_pos = int(pmask.sum())
+    z = logits - logits.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    s = e.sum(axis=1, keepdims=True)
+    pred0 = (e[:, 0:1] / s)[:, 0].astype(f32)
+    nmask = ~pmask
+    nvalues = np.where(nmask, pred0, f32(1.0))
+    max_neg = int(nmask.sum())
+    n_neg = min(int(f32(negative_ratio) * f32(n_pos)) + bs, max_neg)
+    max_hard = np.sort(nvalues, kind="stable")[n_neg - 1] if n_neg > 0 else f32(0)
+    sel = nmask & (nvalues < max_hard)
+    factors = []
+    for iou in iou_layers:
+        v = np.asarray(iou, f32)
+        ax = tuple(range(1, v.ndim))
+        mean = v.mean(axis=ax, keepdims=True, dtype=np.float64).astype(f32)
+        var = ((v - mean) * (v - mean)).mean(axis=ax, keepdims=True, dtype=np.float64).astype(f32)
+        v = (v - mean) / np.sqrt(var + f32(1e-8))
+        v = v + (f32(0.) - v.min(axis=ax, keepdims=True))
+        v = v / (v.max(axis=ax, keepdims=True) + f32(1e-8))
+        factors.append((v ** 4).reshape(-1))
+    factor = np.concatenate(factors).astype(f32)
+    lse = np.log(s[:, 0].astype(np.float64))
+    ce_lab = lse - z[np.arange(z.shape[0]), gcls].astype(np.float64)
+    ce_0 = lse - z[:, 0].astype(np.float64)
+    pos_loss = float(np.sum(ce_lab * pmask * factor.astype(np.float64))) / bs
+    neg_loss = float(np.sum(ce_0 * sel)) / bs
+    w = np.where(pmask, factor.astype(np.float64) / bs, np.where(sel, 0.5 / bs, 0.0))
+    return dict(clf_loss=neg_loss / 2. + pos_loss, pos_loss=pos_loss, neg_loss=neg_loss, max_hard_pred=float(max_hard),
+                n_pos=n_pos, n_neg=n_neg, weights=w, targets=np.where(pmask, gcls, 0), softmax=(e / s))

@@ -456,7 +456,31 @@ def _build_tf_module():
         e = np.exp(a - np.max(a, axis=axis, keepdims=True))
         return Tensor((e / np.sum(e, axis=axis, keepdims=True)).astype(a.dtype))
     nn.softmax = softmax
+
+    def moments(x, axes, shift=None, name=None, keep_dims=False):
+        a = _t(x).a
+        ax = tuple(int(v) for v in axes)
+        mean = np.mean(a, axis=ax, keepdims=True, dtype=a.dtype)
+        var = np.mean((a - mean) * (a - mean), axis=ax, keepdims=True, dtype=a.dtype)    # mean of squared difference
+        if not keep_dims:
+            mean, var = np.squeeze(mean, ax), np.squeeze(var, ax)
+        return Tensor(mean), Tensor(var)
+    nn.moments = moments
+
+    def sparse_softmax_cross_entropy_with_logits(_sentinel=None, labels=None, logits=None, name=None):
+        x = _t(logits).a
+        lab = np.asarray(_unwrap(labels)).astype(np.int64)
+        z = x - np.max(x, axis=-1, keepdims=True)
+        lse = np.log(np.sum(np.exp(z), axis=-1, dtype=x.dtype))
+        return Tensor((lse - np.take_along_axis(z, lab[..., None], axis=-1)[..., 0]).astype(x.dtype))
+    nn.sparse_softmax_cross_entropy_with_logits = sparse_softmax_cross_entropy_with_logits
     tf.nn = nn
+    tf.pow = _bi(np.power)
+    tf.div = lambda x, y, name=None: _t(x) / y
+    # tf.contrib.slim.softmax is executed by det_clf_loss (utils/net_tools.py:571); the rest of contrib is mocked
+    contrib = mock.MagicMock(name="tensorflow.contrib")
+    contrib.slim.softmax = softmax
+    tf.contrib = contrib
 
     # ---- tf.image --------------------------------------------------------- #
     image = types.ModuleType("tensorflow.image")

@@ -72,6 +72,11 @@ SIGNATURES = {
     "rod_precision_recall_workspace_bytes": (_sz, [_i64]),
     "rod_precision_recall": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_average_precision": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "rod_smooth_l1_workspace_bytes": (_sz, [_LP, _i]),
+    "rod_smooth_l1_loss": (_i, [_LP, _YP, _YP, _YP, _i, _vp, _vp, _f, _vp, _sz, _vp]),
+    "rod_clf_loss_workspace_bytes": (_sz, [_LP, _i]),
+    "rod_clf_loss": (_i, [_LP, _YP, _YP, _YP, _YP, _i, _i, _f, _vp, _vp, _sz, _vp]),
+    "rod_clf_loss_grad": (_i, [_LP, _YP, _YP, _YP, _YP, _i, _i, _f, _vp, _vp, _vp]),
     "rod_gt_boxes_update": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

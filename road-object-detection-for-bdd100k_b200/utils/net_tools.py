@@ -403,3 +403,7 @@ def decode_detected_bboxes(anchors_all_layer, refine_out, det_out, predictions, 
     do = [_f32(t, "det_out") for t in det_out]
     return _detect(list(predictions), None, ro, do, anchors_all_layer, select_threshold, nms_threshold,
                    clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits)
+
+
+# --------------------------------------------------------------------------------- f-3 losses
+from .losses import smooth_l1, refine_loss, det_clf_loss  # noqa: E402,F401  (utils/net_tools.py:478-623)

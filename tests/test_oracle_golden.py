@@ -241,3 +241,18 @@ def test_gt_boxes_pipeline_restatement():
             lab, bx = R.gt_boxes_train(z["labels"][b, :n], z["boxes"][b, :n], z["crops"][b], bool(z["mirror"][b]), 0.3, bool(neg))
             assert np.array_equal(lab, z["labels_%d_%d" % (b, neg)]), (b, neg)
             assert bit_equal(bx.reshape(-1, 4), z["bboxes_%d_%d" % (b, neg)]), (b, neg)
+
+
+def test_losses_restatement():
+    """oracle/restated smooth_l1_loss / clf_loss against refine_loss / det_clf_loss of the unmodified reference
+    (utils/net_tools.py:492-623) run by oracle/gen_golden_loss.py (float tolerance 1e-5)."""
+    z = golden("losses.npz")
+    L = int(z["n_layers"])
+    get = lambda k: [z["%s_%d" % (k, l)] for l in range(L)]
+    rl = R.smooth_l1_loss(get("refine_gt"), get("ro"), get("refine_pos"))
+    dl = R.smooth_l1_loss(get("det_gt"), get("do"), get("det_mask"))
+    cl = R.clf_loss(get("clf"), get("det_mask"), get("det_lab"), get("iou"))
+    assert abs(rl - float(z["refine_loss"])) <= 1e-5 * abs(float(z["refine_loss"]))
+    assert abs(dl - float(z["det_loss"])) <= 1e-5 * abs(float(z["det_loss"]))
+    assert abs(cl["clf_loss"] - float(z["clf_loss"])) <= 1e-5 * abs(float(z["clf_loss"]))
+    assert cl["n_pos"] > 0 and cl["n_neg"] == 3 * cl["n_pos"] + 4
