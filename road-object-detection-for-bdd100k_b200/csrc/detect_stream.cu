@@ -644,10 +644,10 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
                     fmaxf(fabsf(c.y), fabsf(c.w)) < __fmul_rn(65536.f, sw);
     return ok ? make_float4(__fadd_rn(c.x, sh), __fadd_rn(c.y, sw), __fsub_rn(c.z, sh), __fsub_rn(c.w, sw)) : c;
   };
-  // ---- 2. gather / decode the m boxes (evaluate.py:141-142), select-stage mask is 1 for all of them
-  for (int j = tid; j < m; j += kSegBlock) {
-    const unsigned long long key = s_keys[j];
-    const int i = (int)(~(unsigned)(key & 0xffffffffull));
+  // ---- 2. gather / decode boxes (evaluate.py:141-142), select-stage mask is 1 for all of them.
+  // Only the first 256 candidates now; the greedy loop usually stops before it needs more (keep_top_k
+  // survivors), and fetches further chunks on demand.  Until then s_area[j] parks the anchor index.
+  auto gather = [&](int j, int i) {
     const int l = layer_of(P.L, i);
     const long long off = 4ll * (i - P.L.offset[l]);
     float4 v;
@@ -667,7 +667,12 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     s_nbox[j] = nbv;
     s_qbox[j] = shrunk(nbv, area);
     s_area[j] = area;
+  };
+  int gathered = 0;
+  for (int j = tid; j < m; j += kSegBlock) {
+    const unsigned long long key = s_keys[j];
     s_score[j] = __uint_as_float((unsigned)(key >> 32));
+    s_area[j] = __int_as_float((int)(~(unsigned)(key & 0xffffffffull)));
   }
   __syncthreads();                                    // keys are dead from here: region A becomes the mask
 
@@ -693,6 +698,12 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     // close to keep_top_k a half batch (one candidate per lane) is enough: the last full batch would
     // spend a quarter of all pair tests on a handful of survivors
     bsz = (keep - nk <= 24) ? 32 : 64;
+    if (p0 + bsz > gathered && gathered < m) {           // block-uniform: fetch the next boxes (256 first, then 128 at a time)
+      const int g1 = min(m, gathered + (gathered == 0 ? 256 : 128));
+      for (int j = gathered + tid; j < g1; j += kSegBlock) gather(j, __float_as_int(s_area[j]));
+      gathered = g1;
+      __syncthreads();
+    }
     const bool two = bsz == 64;
     const int nb = min(bsz, m - p0);
     const int c0 = p0 + lane, c1 = c0 + 32;
