@@ -909,7 +909,8 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   if (C == 11) {
     // ---- TMA-staged single pass (+ dense second pass)
     ScanParams SP;
-    SP.probs = probs; SP.L = L; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;
+    SP.probs = probs; SP.L = L; SP.batch = batch; SP.thr = select_thr;
+    SP.ignore_class = (ignore_class >= 0 && ignore_class < 11) ? ignore_class : 31;   // 31: no class bit ever matches
     SP.g_hist = g_hist; SP.g_cnt1 = g_cnt1; SP.g_cnt2 = g_cnt2; SP.g_flag = g_flag; SP.g_list = g_list;
     SP.g_list2 = g_list2; SP.cap2 = cap; SP.top_k = top_k;
     int chunks = (4 * sm_count() + batch - 1) / batch;          // one wave of ~4 CTAs per SM (8 per SM measured slower: 32 vs 29 us)
