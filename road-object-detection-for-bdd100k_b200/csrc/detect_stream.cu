@@ -148,69 +148,97 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 __device__ __forceinline__ int warp_threshold_bin(const unsigned* __restrict__ hist_row, int k, int lane);
 
+constexpr int kSampleBins = 256;    // coarse bins (4 score bins each) of the sampled histogram
+constexpr int kSampleStride = 8;    // every 8th 256-anchor tile is sampled
+
 struct ScanParams {
   LayeredF probs;
   Layout L;
   int ignore_class, batch, chunk;      // chunk = anchors per CTA (multiple of 256)
   int chunks, spc;                     // CTAs per image, list slots per (class, CTA)
   float thr;
-  unsigned* g_hist;                    // [rows][kBins]
-  unsigned* g_cnt1;                    // [rows][kMaxChunks] candidates written by each sparse-pass CTA
-  unsigned* g_cnt2;                    // [rows] candidates appended by the dense pass
-  unsigned* g_flag;                    // [rows] != 0: some CTA ran out of list slots => dense segment
-  unsigned long long* g_list;          // [rows][kListCap]  sparse-pass slices
-  unsigned long long* g_list2;         // [rows][cap2]      entries at or above the threshold bin
-  int cap2, top_k;
+  unsigned* g_shist;                   // [rows][kSampleBins] histogram of the sampled tiles (sample_kernel)
+  int sample_target;                   // sampled candidates that must lie at or above the estimated cut
+  int* g_est;                          // [rows] estimated cut as a score bin (0: no cut beyond thr)
+  unsigned* g_cnt1;                    // [rows][kMaxChunks] candidates written by each CTA
+  unsigned* g_over;                    // [rows] set when a CTA ran out of list slots: exact general kernels redo the segment
+  unsigned long long* g_list;          // [rows][kListCap]  per-CTA slices
 };
 
-template <int MODE, int C>
+template <int C>
 struct ScanShared {
-  unsigned hist[MODE == 0 ? C * kBins / 2 : 1];                 // two 16-bit counters per word
   unsigned cnt[C];
-  int tb[C];
-  unsigned long long* slice[C];                                 // MODE 0: this CTA's list slice per class
+  float cut[C];                        // per-class append threshold: max(thr, estimated cut)
 };
+
+// probabilities of one anchor in registers: e[] holds the C scores, or (LOGITS, f-1) the logits, which are
+// replaced by their softmax; mx / rinv let a single class be recomputed later with the same instructions
+template <int C, bool LOGITS>
+__device__ __forceinline__ void row_probs(float (&e)[C], float& mx, float& rinv) {
+  if constexpr (LOGITS) {
+    mx = e[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, e[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) e[c] = softmax_exp(e[c], mx);
+    float sum = e[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) sum = __fadd_rn(sum, e[c]);
+    rinv = __frcp_rn(sum);
+#pragma unroll
+    for (int c = 0; c < C; ++c) e[c] = __fmul_rn(e[c], rinv);
+  }
+}
+
+// Pre-pass: histogram (coarse bins) of the candidates of every kSampleStride-th tile.  From it the scan
+// pass estimates, per segment, a score cut above which about 2 * top_k candidates lie, and only appends
+// those.  The estimate cannot affect the result: a segment whose list then holds fewer than top_k entries
+// (or overflows) is redone by the exact general kernels.
+template <int C, bool LOGITS>
+__global__ void __launch_bounds__(256)
+sample_kernel(const __grid_constant__ ScanParams P) {
+  const int b = blockIdx.y;
+  const int n = (blockIdx.x * kSampleStride + kSampleStride / 2) * 256 + threadIdx.x;
+  if (n >= P.L.n_total) return;
+  const int l = layer_of(P.L, n);
+  const float* row = P.probs.base[l] + (long long)b * P.probs.stride[l] + (long long)(n - P.L.offset[l]) * C;
+  float e[C], mx = 0.f, rinv = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) e[c] = __ldg(row + c);
+  row_probs<C, LOGITS>(e, mx, rinv);
+  unsigned cand = 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) cand |= (unsigned)(e[c] >= P.thr) << c;
+  cand &= ~(1u << P.ignore_class);
+  unsigned* h = P.g_shist + (size_t)b * kSampleBins;
+  while (cand) {
+    const int c = __ffs(cand) - 1;
+    cand &= cand - 1;
+    float s = __ldg(row + c);
+    if constexpr (LOGITS) s = __fmul_rn(softmax_exp(s, mx), rinv);
+    atomicAdd(h + (size_t)c * P.batch * kSampleBins + (score_bin(s) >> 2), 1u);
+  }
+}
 
 // One anchor per lane; `row` points at its C scores (shared-memory tile, or global for the few
-// unaligned head / tail anchors).  MODE 0: histogram + append to this CTA's private slice of the
-// segment's list while it has room.  MODE 1: append candidates at or above the threshold bin.
+// unaligned head / tail anchors).  Candidates at or above the class's cut are appended to this CTA's
+// private slice of the segment's list while it has room.
 // LOGITS: the row holds logits; probabilities come from softmax_exp / __frcp_rn (common.cuh), and a
 // candidate's probability is recomputed with the same instructions when its key is built.
-template <int MODE, int C, bool LOGITS>
-__device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE, C>& S, bool valid,
+template <int C, bool LOGITS>
+__device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<C>& S, const float (&cut)[C], bool valid,
                                             const float* __restrict__ row, int n, int b) {
+  unsigned long long* const slice0 = P.g_list + (size_t)b * kListCap + (size_t)blockIdx.x * P.spc;
+  const size_t slice_stride = (size_t)P.batch * kListCap;
   unsigned cand = 0;
   float mx = 0.f, rinv = 0.f;
   if (valid) {
-    if constexpr (LOGITS) {
-      float e[C];
+    float e[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) e[c] = row[c];
-      mx = e[0];
+    for (int c = 0; c < C; ++c) e[c] = row[c];
+    row_probs<C, LOGITS>(e, mx, rinv);
 #pragma unroll
-      for (int c = 1; c < C; ++c) mx = fmaxf(mx, e[c]);
-#pragma unroll
-      for (int c = 0; c < C; ++c) e[c] = softmax_exp(e[c], mx);
-      float sum = e[0];
-#pragma unroll
-      for (int c = 1; c < C; ++c) sum = __fadd_rn(sum, e[c]);
-      rinv = __frcp_rn(sum);
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float s = __fmul_rn(e[c], rinv);
-        bool p = s >= P.thr;
-        if constexpr (MODE == 1) p = p && score_bin(s) >= S.tb[c];
-        cand |= (unsigned)p << c;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float s = row[c];
-        bool p = s >= P.thr;
-        if constexpr (MODE == 1) p = p && score_bin(s) >= S.tb[c];
-        cand |= (unsigned)p << c;
-      }
-    }
+    for (int c = 0; c < C; ++c) cand |= (unsigned)(e[c] >= cut[c]) << c;
     cand &= ~(1u << P.ignore_class);
   }
   const unsigned nkey = (unsigned)(~(unsigned)n);
@@ -219,52 +247,54 @@ __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<MODE
     cand &= cand - 1;
     float s = row[c];
     if constexpr (LOGITS) s = __fmul_rn(softmax_exp(s, mx), rinv);
-    const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | nkey;
-    if constexpr (MODE == 0) {
-      const int bin = score_bin(s);
-      atomicAdd(&S.hist[c * (kBins / 2) + (bin >> 1)], 1u << ((bin & 1) << 4));
-      if (S.cnt[c] < (unsigned)P.spc) {
-        const unsigned pos = atomicAdd(&S.cnt[c], 1u);
-        if (pos < (unsigned)P.spc) S.slice[c][pos] = key;
-      }
-    } else {
-      const size_t r = (size_t)c * P.batch + b;
-      const unsigned pos = atomicAdd(&P.g_cnt2[r], 1u);
-      if (pos < (unsigned)P.cap2) P.g_list2[r * P.cap2 + pos] = key;
+    if (S.cnt[c] < (unsigned)P.spc) {                     // (dense inputs: no atomic once the slice is full)
+      const unsigned pos = atomicAdd(&S.cnt[c], 1u);
+      if (pos < (unsigned)P.spc)
+        slice0[(size_t)c * slice_stride + pos] = ((unsigned long long)__float_as_uint(s) << 32) | nkey;
     }
   }
 }
 
-template <int MODE, int C, bool LOGITS>
+template <int C, bool LOGITS>
 __global__ void __launch_bounds__(kScanBlock)
 scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   float* s_tiles = reinterpret_cast<float*>(s_dyn);                      // kScanStages x [256][C]
-  ScanShared<MODE, C>& S = *reinterpret_cast<ScanShared<MODE, C>*>(s_dyn + kScanStages * sizeof(float) * kScanBlock * C);
+  ScanShared<C>& S = *reinterpret_cast<ScanShared<C>*>(s_dyn + kScanStages * sizeof(float) * kScanBlock * C);
   __shared__ __align__(8) unsigned long long s_bar[kScanStages];
-  __shared__ int s_any;
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
-  if constexpr (MODE == 0) {
-    for (int i = tid; i < C * kBins / 2; i += kScanBlock) S.hist[i] = 0u;
-  }
-  if (tid == 0) s_any = 0;
-  __syncthreads();
-  if (tid < C) {
-    S.cnt[tid] = 0u;
-    S.slice[tid] = P.g_list + ((size_t)tid * P.batch + b) * kListCap + (size_t)blockIdx.x * P.spc;
-  }
-  if constexpr (MODE == 1) {
-    // threshold bins of this image's dense classes, straight from the finished histograms
-    for (int c = tid >> 5; c < C; c += kScanBlock / 32) {
-      const size_t r = (size_t)c * P.batch + b;
-      const bool dense = c != P.ignore_class && P.g_flag[r] != 0u;            // warp-uniform
-      const int t = dense ? warp_threshold_bin(P.g_hist + r * kBins, P.top_k, tid & 31) : 0x7fffffff;
-      if ((tid & 31) == 0) {
-        S.tb[c] = t;
-        if (dense) s_any = 1;
+  if (tid < C) S.cnt[tid] = 0u;
+  // per-class cut from the sampled histogram: the highest coarse bin t with count(bins >= t) >= target
+  for (int c = tid >> 5; c < C; c += kScanBlock / 32) {
+    const int lane = tid & 31;
+    const unsigned* h = P.g_shist + ((size_t)c * P.batch + b) * kSampleBins + lane * 8;
+    unsigned v[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = h[q]; sum += v[q]; }
+    unsigned suf = sum;                                // inclusive suffix over lanes (lane 31 owns the top bins)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += x;
+    }
+    const unsigned above = suf - sum, target = (unsigned)P.sample_target;
+    int t = 0;
+    if (above < target && suf >= target) {             // exactly one lane when the row holds >= target samples
+      unsigned acc = above;
+#pragma unroll
+      for (int q = 7; q >= 0; --q) {
+        acc += v[q];
+        if (acc >= target) { t = lane * 8 + q; break; }
       }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) {
+      const float cut = fmaxf(P.thr, (float)(4 * t) * (1.f / (float)kBins));     // score_bin(s) >= 4t  <=>  s >= 4t / 1024
+      S.cut[c] = cut;
+      if (blockIdx.x == 0) P.g_est[(size_t)c * P.batch + b] = cut > P.thr ? 4 * t : 0;
     }
   }
   if (tid == 0) {
@@ -272,7 +302,9 @@ scan_kernel(const __grid_constant__ ScanParams P) {
     fence_mbar_init();
   }
   __syncthreads();
-  if (MODE == 1 && !s_any) return;                      // no dense segment in this image
+  float cut[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) cut[c] = S.cut[c];
 
   const int A0 = blockIdx.x * P.chunk, A1 = min(A0 + P.chunk, P.L.n_total);
   unsigned phases = 0;                                 // bit q = parity of barrier q
@@ -302,7 +334,7 @@ scan_kernel(const __grid_constant__ ScanParams P) {
     const int nscalar = (t0 - lo) + (hi - t1);
     for (int i = tid; i < nscalar; i += kScanBlock) {
       const int n = i < t0 - lo ? lo + i : t1 + (i - (t0 - lo));
-      scan_anchor<MODE, C, LOGITS>(P, S, true, slab + (long long)n * C, n, b);
+      scan_anchor<C, LOGITS>(P, S, cut, true, slab + (long long)n * C, n, b);
     }
     for (int t = 0; t < ntiles; ++t) {
       const int q = t % kScanStages;
@@ -313,27 +345,16 @@ scan_kernel(const __grid_constant__ ScanParams P) {
       mbar_wait(&s_bar[q], (phases >> q) & 1u);
       phases ^= 1u << q;
       // row stride C words: conflict-free across lanes for odd C
-      scan_anchor<MODE, C, LOGITS>(P, S, tid < cnt, s_tiles + q * kScanBlock * C + tid * C, a0 + tid, b);
+      scan_anchor<C, LOGITS>(P, S, cut, tid < cnt, s_tiles + q * kScanBlock * C + tid * C, a0 + tid, b);
       __syncthreads();                                   // tile consumed: its buffer may be refilled
     }
   }
-  if constexpr (MODE == 0) {
-    __syncthreads();
-    if (tid < C) {
-      const size_t r = (size_t)tid * P.batch + b;
-      const unsigned c = S.cnt[tid];
-      P.g_cnt1[r * kMaxChunks + blockIdx.x] = c < (unsigned)P.spc ? c : (unsigned)P.spc;
-      if (c >= (unsigned)P.spc) P.g_flag[r] = 1u;        // out of slots (conservatively also when exactly full)
-    }
-    for (int i = tid; i < C * kBins / 2; i += kScanBlock) {
-      const unsigned w = S.hist[i];
-      if (w) {
-        const int c = (2 * i) / kBins, bin = 2 * i - c * kBins;
-        unsigned* g = P.g_hist + ((size_t)c * P.batch + b) * kBins + bin;
-        if (w & 0xffffu) atomicAdd(g, w & 0xffffu);
-        if (w >> 16) atomicAdd(g + 1, w >> 16);
-      }
-    }
+  __syncthreads();
+  if (tid < C) {
+    const size_t r = (size_t)tid * P.batch + b;
+    const unsigned c = S.cnt[tid];
+    P.g_cnt1[r * kMaxChunks + blockIdx.x] = c < (unsigned)P.spc ? c : (unsigned)P.spc;
+    if (c >= (unsigned)P.spc) P.g_over[r] = 1u;          // out of slots (conservatively also when exactly full)
   }
 }
 
@@ -444,14 +465,12 @@ struct SegParams {
   int has_loc, batch, ignore_class, cap, k, keep;
   float nms_thr;
   const float* clip;
-  // sparse segments: per-CTA slices of the scan pass ([rows][kListCap], counts [rows][kMaxChunks]),
-  // filtered here against the threshold bin derived from the histogram row;
-  // dense segments (flag != 0 or force_dense): the final list the second pass wrote ([rows][cap], cnt2)
+  // candidate lists: per-CTA slices of the scan pass ([rows][kListCap], counts [rows][kMaxChunks]), or
+  // (force_dense: prediction depths without the TMA scan) one list per segment ([rows][cap], cnt2)
   const unsigned long long* list1;
   const unsigned* cnt1;
-  const unsigned* hist;
-  const unsigned* flag;
   const unsigned* cnt2;
+  const int* est;            // [rows] score bin below which the scan pass dropped candidates (0: none dropped)
   long long* dbg;            // optional per-segment phase timestamps (rod_debug_set_timing), else NULL
   unsigned* over;            // out: 1 when the segment must be redone by the exact general kernels
   int chunks, spc, force_dense;
@@ -512,121 +531,114 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #define SEG_T(i) do { if (P.dbg != nullptr && tid == 0) P.dbg[r * 8 + (i)] = clock64(); } while (0)
   SEG_T(0);
-  // ---- 0. candidates at or above the threshold bin -> s_keys[0, cnt)
+  // ---- 0. histogram of the segment's listed candidates -> threshold bin (the lowest bin still inside
+  // the top_k) and the start offset of every bin in descending order.
   __shared__ int s_n, s_tbv;
   __shared__ unsigned s_part[kMaxChunks];
-  const bool dense = P.force_dense || P.flag[r] != 0u;
-  int cnt;
-  if (dense) {                                        // already filtered by the second pass
+  __shared__ unsigned s_wsum[kSegWarps];
+  const bool dense = P.force_dense != 0;
+  const unsigned long long* base;
+  int parts, pstride, maxc;
+  if (dense) {
     const unsigned n_in = P.cnt2[r];
     if (n_in > (unsigned)cap) {                       // massive ties in the threshold bin: exact kernels redo it
       if (tid == 0) P.over[r] = 1u;
       return;
     }
-    cnt = (int)n_in;
-    for (int j = tid; j < cnt; j += kSegBlock) s_keys[j] = g_list[r * cap + j];
+    base = g_list + r * cap; parts = 1; pstride = 0; maxc = (int)n_in;
+    if (tid == 0) s_part[0] = n_in;
   } else {
-    if (tid < P.chunks) s_part[tid] = P.cnt1[r * kMaxChunks + tid];
-    if (tid == 0) s_n = 0;
-    if (warp == kSegWarps - 1) {                      // smallest bin with count(bins >= t) >= k
-      const int t = warp_threshold_bin(P.hist + r * kBins, k, lane);
-      if (lane == 0) s_tbv = t;
-    }
-    __syncthreads();
-    const int tb = s_tbv;
-    const unsigned long long* base = P.list1 + r * kListCap;
-    // four slices (<= 512 entries each, two per thread) per round: 8 independent loads in flight
-    for (int p0 = 0; p0 < P.chunks; p0 += 4) {
+    if (P.over[r] != 0u) return;                      // a scan CTA ran out of list slots: exact kernels redo it
+    base = P.list1 + r * kListCap; parts = P.chunks; pstride = P.spc; maxc = P.spc;
+    if (tid < parts) s_part[tid] = P.cnt1[r * kMaxChunks + tid];
+  }
+  const int nsub = (maxc + kSegBlock - 1) / kSegBlock;                   // 256-entry rounds per slice (1-2; dense: up to 8)
+  unsigned long long* s_tmp = s_keys + cap;
+  unsigned* s_h = reinterpret_cast<unsigned*>(s_keys + 2 * cap);          // [kBins]
+  for (int i = tid; i < kBins; i += kSegBlock) s_h[i] = 0u;
+  __syncthreads();
+  // entries sub * 256 + tid of eight consecutive slices: eight independent loads in flight per thread
+  auto load8 = [&](int part0, int sub, unsigned long long (&ev)[8]) {
+    const unsigned j = (unsigned)(sub * kSegBlock + tid);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      ev[u] = (part0 + u < parts && j < s_part[part0 + u]) ? base[(size_t)(part0 + u) * pstride + j] : 0ull;
+  };
+  // empty slots are 0 (score +0.0): real entries have score >= thr > 0
+  for (int sub = 0; sub < nsub; ++sub)
+    for (int part0 = 0; part0 < parts; part0 += 8) {
       unsigned long long ev[8];
+      load8(part0, sub, ev);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if ((unsigned)(ev[u] >> 32) != 0u) atomicAdd(&s_h[score_bin(__uint_as_float((unsigned)(ev[u] >> 32)))], 1u);
+    }
+  __syncthreads();
+  {
+    // suffix sums over bins (higher bins first): thread t owns bins [4t, 4t+4)
+    static_assert(kBins == 4 * kSegBlock, "one thread per four bins");
+    const unsigned h0 = s_h[4 * tid], h1 = s_h[4 * tid + 1], h2 = s_h[4 * tid + 2], h3 = s_h[4 * tid + 3];
+    const unsigned mine = h0 + h1 + h2 + h3;
+    unsigned suf = mine;                               // inclusive suffix over the warp's higher lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += x;
+    }
+    if (lane == 0) s_wsum[warp] = suf;
+    __syncthreads();
+    unsigned above = suf - mine;
+    for (int w = warp + 1; w < kSegWarps; ++w) above += s_wsum[w];
+    const unsigned c3 = above + h3, c2 = c3 + h2, c1 = c2 + h1, c0 = c1 + h0;     // count(bins >= 4t+3 .. 4t)
+    const unsigned kk = (unsigned)k;
+    if (above < kk && c0 >= kk) {                      // exactly one thread: the k-th candidate is in my bins
+      const int q = c3 >= kk ? 3 : (c2 >= kk ? 2 : (c1 >= kk ? 1 : 0));
+      s_tbv = 4 * tid + q;
+      s_n = (int)(q == 3 ? c3 : (q == 2 ? c2 : (q == 1 ? c1 : c0)));
+    } else if (tid == 0 && c0 < kk) {                  // fewer than k listed candidates: all of them
+      s_tbv = 0;
+      s_n = (int)c0;
+    }
+    s_h[4 * tid + 3] = above;                          // start offset of every bin in the sorted order
+    s_h[4 * tid + 2] = c3;
+    s_h[4 * tid + 1] = c2;
+    s_h[4 * tid] = c1;
+  }
+  __syncthreads();
+  const int cnt = s_n, tb = s_tbv;
+  // fewer than k listed although the scan pass dropped candidates below its estimated cut (the estimate
+  // was too high), or massive ties in the threshold bin: the exact general kernels redo the segment
+  if ((!dense && cnt < k && P.est[r] > 0) || cnt > cap) {
+    if (tid == 0) P.over[r] = 1u;
+    return;
+  }
+  SEG_T(1);
+  // ---- 1. sort: descending (score bits, ~anchor) = tf.nn.top_k order.  Counting sort on the score
+  // bins (monotone in the score): scatter the entries at or above the threshold bin to their bin's
+  // range, then an exact rank inside each bin (bins hold a handful of entries; all-tied inputs stay
+  // correct, just slower).
+  for (int sub = 0; sub < nsub; ++sub)
+    for (int part0 = 0; part0 < parts; part0 += 8) {
+      unsigned long long ev[8];
+      load8(part0, sub, ev);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int part = p0 + (u >> 1);
-        const unsigned j = (u & 1) * kSegBlock + tid;
-        ev[u] = (part < P.chunks && j < s_part[part]) ? base[(size_t)part * P.spc + j] : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        // empty slots are 0 (score +0.0 -> bin 0, anchor ~0): real entries have score >= thr > 0
-        if ((unsigned)(ev[u] >> 32) != 0u && score_bin(__uint_as_float((unsigned)(ev[u] >> 32))) >= tb) {
-          const int pos = atomicAdd(&s_n, 1);
-          if (pos < cap) s_keys[pos] = ev[u];
+        if ((unsigned)(ev[u] >> 32) != 0u) {
+          const int bin = score_bin(__uint_as_float((unsigned)(ev[u] >> 32)));
+          if (bin >= tb) s_tmp[atomicAdd(&s_h[bin], 1u)] = ev[u];
         }
       }
     }
-    __syncthreads();
-    cnt = s_n;
-    if (cnt > cap) {                                  // massive ties in the threshold bin
-      if (tid == 0) P.over[r] = 1u;
-      return;
-    }
+  __syncthreads();                                    // now s_h[bin] = end of the bin's range = start of bin - 1's
+  for (int j = tid; j < cnt; j += kSegBlock) {
+    const unsigned long long e = s_tmp[j];
+    const int bin = score_bin(__uint_as_float((unsigned)(e >> 32)));
+    const int s0 = bin < kBins - 1 ? (int)s_h[bin + 1] : 0, s1 = (int)s_h[bin];
+    int rank = 0;
+    for (int x = s0; x < s1; ++x) rank += (s_tmp[x] > e) ? 1 : 0;
+    s_keys[s0 + rank] = e;
   }
-
-  SEG_T(1);
-  // ---- 1. sort the candidate list: descending (score bits, ~anchor) = tf.nn.top_k order.
-  // Counting sort on the 1024 score bins the histogram pass already uses (monotone in the score),
-  // then an exact rank inside each bin (bins hold a handful of entries; all-tied inputs stay
-  // correct, just slower).  Four block-wide steps instead of a 45-step bitonic network.
-  {
-    constexpr int kPer = (2 * ROD_MAX_TOPK + kSegBlock - 1) / kSegBlock;   // list entries per thread (cap <= 2048)
-    unsigned long long* s_tmp = s_keys + cap;
-    unsigned* s_h = reinterpret_cast<unsigned*>(s_keys + 2 * cap);        // [kBins]
-    __shared__ unsigned s_wsum[kSegWarps];
-    for (int i = tid; i < kBins; i += kSegBlock) s_h[i] = 0u;
-    __syncthreads();
-    unsigned long long ev[kPer];
-    int ebin[kPer];
-    unsigned erk[kPer];
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int j = tid + q * kSegBlock;
-      if (j < cnt) {
-        ev[q] = s_keys[j];
-        ebin[q] = score_bin(__uint_as_float((unsigned)(ev[q] >> 32)));
-        erk[q] = atomicAdd(&s_h[ebin[q]], 1u);
-      }
-    }
-    __syncthreads();
-    // exclusive suffix sum over bins (higher bins first): thread t owns bins [4t, 4t+4)
-    {
-      static_assert(kBins == 4 * kSegBlock, "one thread per four bins");
-      const unsigned h0 = s_h[4 * tid], h1 = s_h[4 * tid + 1], h2 = s_h[4 * tid + 2], h3 = s_h[4 * tid + 3];
-      const unsigned mine = h0 + h1 + h2 + h3;
-      unsigned suf = mine;                             // inclusive suffix over the warp's higher lanes
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
-        if (lane + o < 32) suf += x;
-      }
-      if (lane == 0) s_wsum[warp] = suf;
-      __syncthreads();
-      unsigned above = suf - mine;
-      for (int w = warp + 1; w < kSegWarps; ++w) above += s_wsum[w];
-      s_h[4 * tid + 3] = above;                        // start offset of every bin in the sorted order
-      s_h[4 * tid + 2] = above + h3;
-      s_h[4 * tid + 1] = above + h3 + h2;
-      s_h[4 * tid] = above + h3 + h2 + h1;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int j = tid + q * kSegBlock;
-      if (j < cnt) s_tmp[s_h[ebin[q]] + erk[q]] = ev[q];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int j = tid + q * kSegBlock;
-      if (j < cnt) {
-        const unsigned long long e = s_tmp[j];
-        const int bin = score_bin(__uint_as_float((unsigned)(e >> 32)));
-        const int s0 = (int)s_h[bin], s1 = bin > 0 ? (int)s_h[bin - 1] : cnt;
-        int rank = 0;
-        for (int x = s0; x < s1; ++x) rank += (s_tmp[x] > e) ? 1 : 0;
-        s_keys[s0 + rank] = e;
-      }
-    }
-    __syncthreads();
-  }
+  __syncthreads();
   SEG_T(2);
   const int m = min(cnt, k);                          // real candidates entering NMS
 
@@ -874,7 +886,7 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t stream_workspace_bytes(int batch, int n_classes, int top_k) {
   const size_t rows = (size_t)batch * n_classes;
-  return align256(rows * kBins * 4 + rows * 4 * 3) + align256(rows * 4) + align256(rows * kMaxChunks * 4) +
+  return align256(rows * (4 + 4 + kSampleBins * 4 + kBins * 4)) + align256(rows * 4) + align256(rows * kMaxChunks * 4) +
          align256(rows * (size_t)kListCap * 8) + align256(rows * (size_t)stream_cap(top_k) * 8) + 256;
 }
 
@@ -889,51 +901,63 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   const size_t rows = (size_t)batch * C;
   const int cap = stream_cap(top_k);
   unsigned char* p = reinterpret_cast<unsigned char*>(ws);
-  unsigned* g_hist = reinterpret_cast<unsigned*>(p);
-  unsigned* g_cnt2 = g_hist + rows * kBins;
-  unsigned* g_flag = g_cnt2 + rows;
-  unsigned* g_over = g_flag + rows;
-  const size_t zero_bytes = rows * kBins * 4 + rows * 4 * 3;
-  p += align256(zero_bytes);
-  int* g_tbin = reinterpret_cast<int*>(p);
+  // zero-initialised head of the workspace: over flags, dense counters, sampled histogram (TMA path) and the
+  // full histogram (plain-load path only)
+  unsigned* g_over = reinterpret_cast<unsigned*>(p);
+  unsigned* g_cnt2 = g_over + rows;
+  unsigned* g_shist = g_cnt2 + rows;
+  unsigned* g_hist = g_shist + rows * kSampleBins;
+  const size_t zero_tma = rows * (4 + 4 + kSampleBins * 4), zero_all = zero_tma + rows * kBins * 4;
+  p += align256(zero_all);
+  int* g_tbin = reinterpret_cast<int*>(p);                     // plain-load path: threshold bins; TMA path: estimated cuts
   p += align256(rows * 4);
-  unsigned* g_cnt1 = reinterpret_cast<unsigned*>(p);           // [rows][kMaxChunks], fully written by A1
+  unsigned* g_cnt1 = reinterpret_cast<unsigned*>(p);           // [rows][kMaxChunks], fully written by the scan pass
   p += align256(rows * kMaxChunks * 4);
   unsigned long long* g_list = reinterpret_cast<unsigned long long*>(p);
   p += align256(rows * (size_t)kListCap * 8);
   unsigned long long* g_list2 = reinterpret_cast<unsigned long long*>(p);   // [rows][cap]
   int n_chunks = 1, spc = 512, force_dense = 0;
-  ROD_CUDA(cudaMemsetAsync(g_hist, 0, zero_bytes, st));
+  ROD_CUDA(cudaMemsetAsync(g_over, 0, C == 11 ? zero_tma : zero_all, st));
   if (out_counts) ROD_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * rows, st));
 
   if (C == 11) {
-    // ---- TMA-staged single pass (+ dense second pass)
+    // ---- sampled pre-pass + TMA-staged single pass
     ScanParams SP;
     SP.probs = probs; SP.L = L; SP.batch = batch; SP.thr = select_thr;
     SP.ignore_class = (ignore_class >= 0 && ignore_class < 11) ? ignore_class : 31;   // 31: no class bit ever matches
-    SP.g_hist = g_hist; SP.g_cnt1 = g_cnt1; SP.g_cnt2 = g_cnt2; SP.g_flag = g_flag; SP.g_list = g_list;
-    SP.g_list2 = g_list2; SP.cap2 = cap; SP.top_k = top_k;
-    int chunks = (4 * sm_count() + batch - 1) / batch;          // one wave of ~4 CTAs per SM (8 per SM measured slower: 32 vs 29 us)
+    SP.g_shist = g_shist; SP.g_est = g_tbin; SP.g_cnt1 = g_cnt1; SP.g_over = g_over; SP.g_list = g_list;
+    // sampled tiles: kSampleStride/2, kSampleStride/2 + kSampleStride, ... ; the cut keeps about 2 * top_k
+    // candidates per segment (5 sigma above top_k for a binomial sample of 1/8)
+    const int ntiles = (L.n_total + 255) / 256;
+    const int stiles = (ntiles + kSampleStride / 2) / kSampleStride;
+    long long sampled = 0;
+    for (int t = 0; t < stiles; ++t) {
+      const long long a0 = (long long)(t * kSampleStride + kSampleStride / 2) * 256;
+      if (a0 < L.n_total) sampled += (L.n_total - a0 < 256 ? L.n_total - a0 : 256);
+    }
+    const double frac = L.n_total > 0 ? (double)sampled / (double)L.n_total : 0.0;
+    SP.sample_target = (int)(2.0 * top_k * frac + 0.5);
+    if (SP.sample_target < 32 || stiles < 2) SP.sample_target = 0x7fffffff;      // too few samples: never cut
+    int chunks = (4 * sm_count() + batch - 1) / batch;          // one wave of ~4 CTAs per SM (8 per SM measured slower)
     chunks = chunks < 8 ? 8 : (chunks > 32 ? 32 : chunks);     // >= 8: list slices of at most 512 entries
     int chunk = (L.n_total + chunks - 1) / chunks;
     chunk = ((chunk + kScanBlock - 1) / kScanBlock) * kScanBlock;
-    if (chunk > 61440) chunk = 61440;                           // 16-bit packed histogram counters per CTA
     chunks = (L.n_total + chunk - 1) / chunk;
     ROD_REQUIRE(chunks <= kMaxChunks, "rod_detect: %d anchors need more than %d CTAs per image", L.n_total, kMaxChunks);
     SP.chunk = chunk;
     SP.chunks = n_chunks = chunks;
     SP.spc = spc = kListCap / chunks < 512 ? kListCap / chunks : 512;
+    if (SP.sample_target != 0x7fffffff) {
+      auto ks = logits ? sample_kernel<11, true> : sample_kernel<11, false>;
+      ks<<<dim3(stiles, batch), 256, 0, st>>>(SP);
+      ROD_LAUNCH_CHECK("sample_kernel");
+    }
     const dim3 grid(chunks, batch);
-    const size_t tile_bytes = kScanStages * sizeof(float) * kScanBlock * 11;
-    const size_t smem0 = tile_bytes + sizeof(ScanShared<0, 11>), smem1 = tile_bytes + sizeof(ScanShared<1, 11>);
-    auto k0 = logits ? scan_kernel<0, 11, true> : scan_kernel<0, 11, false>;
-    auto k1 = logits ? scan_kernel<1, 11, true> : scan_kernel<1, 11, false>;
+    const size_t smem0 = kScanStages * sizeof(float) * kScanBlock * 11 + sizeof(ScanShared<11>);
+    auto k0 = logits ? scan_kernel<11, true> : scan_kernel<11, false>;
     ROD_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-    ROD_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     k0<<<grid, kScanBlock, smem0, st>>>(SP);
-    ROD_LAUNCH_CHECK("scan_kernel<0>");
-    k1<<<grid, kScanBlock, smem1, st>>>(SP);
-    ROD_LAUNCH_CHECK("scan_kernel<1>");
+    ROD_LAUNCH_CHECK("scan_kernel");
   } else {
     // ---- generic prediction depth: plain-load two-pass kernels, every segment takes the dense route
     force_dense = 1;
@@ -967,7 +991,7 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   G.L = L; G.batch = batch; G.ignore_class = ignore_class; G.cap = cap; G.k = top_k; G.keep = keep;
   G.nms_thr = nms_thr; G.clip = clip;
   G.cnt2 = g_cnt2; G.over = g_over; G.dbg = g_seg_dbg;
-  G.list1 = g_list; G.cnt1 = g_cnt1; G.hist = g_hist; G.flag = g_flag;
+  G.list1 = g_list; G.cnt1 = g_cnt1; G.est = g_tbin;
   G.chunks = n_chunks; G.spc = spc; G.force_dense = force_dense;
   const size_t smem = seg_smem_bytes(cap, top_k, keep);
   ROD_REQUIRE(smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep, smem);

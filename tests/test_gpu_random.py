@@ -317,3 +317,30 @@ def test_arm_gt_count_extremes(env):
                                     torch.from_numpy(labels[0]).to(env.dev), JB)
     assert tuple(one[0][0].shape) == table.shapes[0] + (4,)
     assert bit_equal(flat_from_list([t.unsqueeze(0) for t in one[0]], 1)[0], g[0][0])
+
+
+@pytest.mark.parametrize("where", ["sampled_only", "unsampled_only"])
+def test_detect_unrepresentative_sample(env, where):
+    """The scan pass cuts candidates below a score estimated from every 8th 256-anchor tile.  Put one class's
+    candidates only INTO those tiles (the estimate overshoots: fewer than top_k survive the cut) or only
+    OUTSIDE them (no estimate at all): the result must still be exact (general kernels / uncut lists)."""
+    layout, B = "512", 2
+    table = env.otable[layout]
+    probs, ro, do = _detect_inputs(env, layout, 800, B, stress=False)
+    tile = np.arange(table.n) // 256
+    sampled = (tile % 8) == 4
+    rng = np.random.default_rng(5)
+    col = np.full((B, table.n), 0.01, np.float32)
+    sel = sampled if where == "sampled_only" else ~sampled
+    col[:, sel] = rng.uniform(0.3, 1.0, size=(B, int(sel.sum()))).astype(np.float32)
+    probs[:, :, 3] = col
+    preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+    rs, rb, counts = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=0.3,
+                                                   nms_threshold=0.45, top_k=400, keep_top_k=200, return_counts=True)
+    o_s, o_b = R.detected_bboxes(probs, R.decode_corner(table, ro, do), 0.3, 0.45, None, 400, 200)
+    for c in range(1, 11):
+        assert bit_equal(rs[c].cpu().numpy(), o_s[c]), c
+        assert bit_equal(rb[c].cpu().numpy(), o_b[c]), c
+        assert np.array_equal(counts[c].cpu().numpy(), (o_s[c] != 0).sum(1))
+    assert (o_s[3] != 0).sum() == B * 200
