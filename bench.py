@@ -568,7 +568,7 @@ def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                         "frac": alg_bytes / (ms / steps * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes_per_step": alg_bytes,
                         "scope": "whole step (scan + segment kernels)"},
-           "gpu_launches": 5 * steps, "kernels_per_step": ["scan_kernel<0,11>", "scan_kernel<1,11>", "segment_kernel", "topk_segment_kernel (overflow only)", "nms_kernel (overflow only)"], "detections_per_image": float(sets[0]["out"][2].sum().item()) / B}
+           "gpu_launches": 5 * steps, "kernels_per_step": ["sample_kernel", "scan_kernel", "segment_kernel", "topk_segment_kernel (flagged segments only)", "nms_kernel (flagged segments only)"], "detections_per_image": float(sets[0]["out"][2].sum().item()) / B}
 
     # e2e through the public API with pinned host inputs and results read back
     p, ro, do = sets[0]["host"]

@@ -5,24 +5,23 @@
 // With thr > 0 every entry the select stage zeroes (score*0, box*0) ranks below every real
 // candidate and is indistinguishable from pad_axis's zero padding in the output, so only the
 // candidates with p >= thr matter.  Per (class, image) segment:
-//   A1  scan_kernel<0>  ONE pass over the [B,N,C] scores (or logits: <.,.,true> computes the softmax of
-//                       each anchor in registers first, f-1).  256-anchor tiles are staged into shared
-//                       memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered); one
-//                       thread per anchor.  Candidates (p >= thr) are counted in a per-segment 1024-bin
-//                       histogram (packed 16-bit shared-memory counters, flushed once per CTA) and
-//                       appended to this CTA's private slice of the segment's candidate list while the
-//                       slice has room.  A segment with a full slice is flagged "dense".
-//   A2  scan_kernel<1>  only for dense segments: second pass that appends the candidates at or above
-//                       the threshold bin, which it derives from the finished histogram itself (the
-//                       NMS-stress workload takes this route).
-//   B   segment_kernel  one CTA per segment: threshold bin from the histogram, filter the list, counting
-//                       sort on the score bins + exact in-bin rank (score desc, anchor asc = tf.nn.top_k
-//                       order), keep the first top_k, gather + decode their boxes, greedy NMS in batches
-//                       against the kept list, write keep_top_k rows zero padded.
-// A list that overflows the sort capacity (massive score ties at the threshold bin) is left to the
-// exact general kernels (topk_segment_kernel + nms_kernel), which re-run only for flagged segments.
+//   S   sample_kernel   coarse histogram of the candidates of every 8th 256-anchor tile (1/8 of the data).
+//   A   scan_kernel     ONE pass over the [B,N,C] scores (or logits: <.,true> computes the softmax of each
+//                       anchor in registers first, f-1).  256-anchor tiles are staged into shared memory
+//                       with TMA bulk copies (cp.async.bulk + mbarrier, double buffered); one thread per
+//                       anchor.  Every CTA derives, per class, a score cut from the sampled histogram such
+//                       that about 2 * top_k candidates of the segment lie above it, and appends the
+//                       candidates above max(thr, cut) to its private slice of the segment's list.
+//   B   segment_kernel  one CTA per segment: histogram of the listed candidates -> threshold bin (the lowest
+//                       bin still inside the top_k), counting sort on the score bins + exact in-bin rank
+//                       (score desc, anchor asc = tf.nn.top_k order), keep the first top_k, gather + decode
+//                       their boxes on demand, greedy NMS in batches against the kept list, write keep_top_k
+//                       rows zero padded.
+// The cut is a performance device only: a segment whose list ends up with fewer than top_k entries although
+// candidates were cut, whose slice overflowed, or whose threshold bin holds massive ties, is flagged and
+// redone by the exact general kernels (topk_segment_kernel + nms_kernel), which run only for flagged rows.
 // Prediction depths other than 11 use the plain-load two-pass kernels (hist_kernel, thresh_kernel,
-// collect_kernel) in front of the same segment kernel.
+// collect_kernel: full histogram, exact threshold bin) in front of the same segment kernel.
 #include "select_topk.cuh"
 
 namespace rod {
@@ -145,8 +144,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
   } while (!ok);
 }
-
-__device__ __forceinline__ int warp_threshold_bin(const unsigned* __restrict__ hist_row, int k, int lane);
 
 constexpr int kSampleBins = 256;    // coarse bins (4 score bins each) of the sampled histogram
 constexpr int kSampleStride = 8;    // every 8th 256-anchor tile is sampled
@@ -358,42 +355,6 @@ scan_kernel(const __grid_constant__ ScanParams P) {
   }
 }
 
-// smallest bin t with count(bins >= t) >= k (0 when the row holds fewer than k); whole warp, uniform result
-__device__ __forceinline__ int warp_threshold_bin(const unsigned* __restrict__ hist_row, int k, int lane) {
-  const uint4* h = reinterpret_cast<const uint4*>(hist_row + lane * 32);
-  unsigned v[32];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const uint4 x = h[q];
-    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-  }
-  unsigned sum = 0;
-#pragma unroll
-  for (int q = 0; q < 32; ++q) sum += v[q];
-  unsigned suf = sum;                                 // inclusive suffix sum (lane 31 owns the top bins)
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
-    if (lane + o < 32) suf += x;
-  }
-  const unsigned above = suf - sum;
-  const unsigned total = __shfl_sync(0xffffffffu, suf, 0);
-  int t = 0;
-  if (total >= (unsigned)k && above < (unsigned)k && suf >= (unsigned)k) {
-    unsigned acc = above;
-    t = lane * 32;
-#pragma unroll
-    for (int q = 31; q >= 0; --q) {
-      acc += v[q];
-      if (acc >= (unsigned)k) { t = lane * 32 + q; break; }
-    }
-  }
-  // exactly one lane found it (or none when total < k): max-reduce
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
-  return t;
-}
-
 // one warp per segment: the smallest bin t with count(bins >= t) >= k  (0 when fewer than k candidates)
 __global__ void __launch_bounds__(256)
 thresh_kernel(const unsigned* __restrict__ g_hist, int rows, int k, int* __restrict__ tbin) {
@@ -488,13 +449,6 @@ __host__ __device__ inline size_t seg_region_a(int cap, int k, int keep) {
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
-// one bitonic compare-exchange between lanes `lane` and `lane ^ stride` (element index e)
-__device__ __forceinline__ unsigned long long bitonic_cx(unsigned long long v, int e, int lane, int size, int stride) {
-  const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, stride);
-  const bool take_max = (((e & size) == 0) == ((lane & stride) == 0));
-  return take_max ? (v > o ? v : o) : (v < o ? v : o);
-}
-
 // exact "fdiv_rn(inter, den) > thr" with a division-free fast path (thr >= 0, den > 0)
 __device__ __forceinline__ bool iou_exceeds(float inter, float den, float thr) {
   const float p = __fmul_rn(thr, den);
@@ -538,41 +492,45 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   __shared__ unsigned s_wsum[kSegWarps];
   const bool dense = P.force_dense != 0;
   const unsigned long long* base;
-  int parts, pstride, maxc;
+  int parts, pstride;
   if (dense) {
     const unsigned n_in = P.cnt2[r];
     if (n_in > (unsigned)cap) {                       // massive ties in the threshold bin: exact kernels redo it
       if (tid == 0) P.over[r] = 1u;
       return;
     }
-    base = g_list + r * cap; parts = 1; pstride = 0; maxc = (int)n_in;
+    base = g_list + r * cap; parts = 1; pstride = 0;
     if (tid == 0) s_part[0] = n_in;
   } else {
     if (P.over[r] != 0u) return;                      // a scan CTA ran out of list slots: exact kernels redo it
-    base = P.list1 + r * kListCap; parts = P.chunks; pstride = P.spc; maxc = P.spc;
+    base = P.list1 + r * kListCap; parts = P.chunks; pstride = P.spc;
     if (tid < parts) s_part[tid] = P.cnt1[r * kMaxChunks + tid];
   }
-  const int nsub = (maxc + kSegBlock - 1) / kSegBlock;                   // 256-entry rounds per slice (1-2; dense: up to 8)
   unsigned long long* s_tmp = s_keys + cap;
   unsigned* s_h = reinterpret_cast<unsigned*>(s_keys + 2 * cap);          // [kBins]
   for (int i = tid; i < kBins; i += kSegBlock) s_h[i] = 0u;
   __syncthreads();
-  // entries sub * 256 + tid of eight consecutive slices: eight independent loads in flight per thread
-  auto load8 = [&](int part0, int sub, unsigned long long (&ev)[8]) {
-    const unsigned j = (unsigned)(sub * kSegBlock + tid);
+  // Visits every listed entry: a warp takes whole slices (a slice holds ~100 entries once the scan pass cuts
+  // at ~2 * top_k per segment), four independent loads per lane; a single long list is split over the block.
+  auto for_each_entry = [&](auto&& fn) {
+    const int stride = parts == 1 ? kSegBlock : 32, first = parts == 1 ? tid : lane;
+    for (int part = parts == 1 ? 0 : warp; part < parts; part += kSegWarps) {
+      const unsigned n = s_part[part];
+      const unsigned long long* sl = base + (size_t)part * pstride;
+      for (unsigned j0 = 0; j0 < n; j0 += 4 * stride) {
+        unsigned long long ev[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      ev[u] = (part0 + u < parts && j < s_part[part0 + u]) ? base[(size_t)(part0 + u) * pstride + j] : 0ull;
-  };
-  // empty slots are 0 (score +0.0): real entries have score >= thr > 0
-  for (int sub = 0; sub < nsub; ++sub)
-    for (int part0 = 0; part0 < parts; part0 += 8) {
-      unsigned long long ev[8];
-      load8(part0, sub, ev);
+        for (int u = 0; u < 4; ++u) {
+          const unsigned j = j0 + u * stride + first;
+          ev[u] = j < n ? sl[j] : 0ull;
+        }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if ((unsigned)(ev[u] >> 32) != 0u) atomicAdd(&s_h[score_bin(__uint_as_float((unsigned)(ev[u] >> 32)))], 1u);
+        for (int u = 0; u < 4; ++u)
+          if ((unsigned)(ev[u] >> 32) != 0u) fn(ev[u]);   // empty slots are 0; real entries have score >= thr > 0
+      }
     }
+  };
+  for_each_entry([&](unsigned long long e) { atomicAdd(&s_h[score_bin(__uint_as_float((unsigned)(e >> 32)))], 1u); });
   __syncthreads();
   {
     // suffix sums over bins (higher bins first): thread t owns bins [4t, 4t+4)
@@ -617,18 +575,10 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   // bins (monotone in the score): scatter the entries at or above the threshold bin to their bin's
   // range, then an exact rank inside each bin (bins hold a handful of entries; all-tied inputs stay
   // correct, just slower).
-  for (int sub = 0; sub < nsub; ++sub)
-    for (int part0 = 0; part0 < parts; part0 += 8) {
-      unsigned long long ev[8];
-      load8(part0, sub, ev);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if ((unsigned)(ev[u] >> 32) != 0u) {
-          const int bin = score_bin(__uint_as_float((unsigned)(ev[u] >> 32)));
-          if (bin >= tb) s_tmp[atomicAdd(&s_h[bin], 1u)] = ev[u];
-        }
-      }
-    }
+  for_each_entry([&](unsigned long long e) {
+    const int bin = score_bin(__uint_as_float((unsigned)(e >> 32)));
+    if (bin >= tb) s_tmp[atomicAdd(&s_h[bin], 1u)] = e;
+  });
   __syncthreads();                                    // now s_h[bin] = end of the bin's range = start of bin - 1's
   for (int j = tid; j < cnt; j += kSegBlock) {
     const unsigned long long e = s_tmp[j];
@@ -890,7 +840,7 @@ size_t stream_workspace_bytes(int batch, int n_classes, int top_k) {
          align256(rows * (size_t)kListCap * 8) + align256(rows * (size_t)stream_cap(top_k) * 8) + 256;
 }
 
-// Enqueues A1, T, A2, B.  *over_out (device, [rows]) is non-zero for segments the exact general
+// Enqueues S, A, B.  *over_out (device, [rows]) is non-zero for segments the exact general
 // kernels must redo.
 int launch_detect_stream(const Layout& L, const float* anchors_center, const LayeredF& probs, const LayeredF* loc,
                          const LayeredF* refine, const LayeredF* det, int batch, int C, int logits, int ignore_class,
