@@ -1,4 +1,6 @@
 """The C oracle port (multi-threaded CPU baseline) against the NumPy restatement: bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -48,3 +50,20 @@ def test_c_oracle_detect(table, stress):
     for c in range(1, 11):
         assert bit_equal(s[c], o_s[c]) and bit_equal(bx[c], o_b[c]), c
     assert C.threads() >= 1
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver times) needs no GPU: one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
