@@ -131,6 +131,22 @@ def test_signatures_match_reference():
     assert params(tfe.safe_divide) == [("numerator", E), ("denominator", E), ("name", None)]
     assert params(common_tools.centerBboxes_2_cornerBboxes) == [("center_bboxes", E)]
     assert params(common_tools.cornerBboxes_2_centerBboxes) == [("corner_bboxes", E)]
+    # the "next" rows of SURVEY.md section 8 (f-1 .. f-4)
+    import torch
+    from rodet_b200.utils.tf_extended import tf_utils
+    assert params(tfe.bboxes_matching, 7) == [("label", E), ("scores", E), ("bboxes", E), ("glabels", E), ("gbboxes", E), ("gdifficults", E), ("matching_threshold", 0.5)]
+    assert params(tfe.bboxes_matching_batch, 7) == [("labels", E), ("scores", E), ("bboxes", E), ("glabels", E), ("gbboxes", E), ("gdifficults", E), ("matching_threshold", 0.5)]
+    assert params(tfe.streaming_tp_fp_arrays, 8) == [("num_gbboxes", E), ("tp", E), ("fp", E), ("scores", E), ("remove_zero_scores", True), ("metrics_collections", None), ("updates_collections", None), ("name", None)]
+    assert params(tfe.precision_recall) == [("num_gbboxes", E), ("num_detections", E), ("tp", E), ("fp", E), ("scores", E), ("dtype", torch.float64), ("scope", None)]
+    assert params(tfe.average_precision_voc07) == [("precision", E), ("recall", E), ("name", None)]
+    assert params(tfe.average_precision_voc12) == [("precision", E), ("recall", E), ("name", None)]
+    assert params(tfe.precision_recall_values) == [("xvals", E), ("precision", E), ("recall", E), ("name", None)]
+    assert params(tfe.cummax) == [("x", E), ("reverse", False), ("name", None)]
+    assert params(tfe.bboxes_filter_overlap) == [("labels", E), ("bboxes", E), ("threshold", 0.5), ("assign_negative", False), ("scope", None)]
+    assert params(tf_utils.reshape_list) == [("l", E), ("shape", None)]
+    assert params(net_tools.smooth_l1) == [("x", E)]
+    assert params(net_tools.refine_loss) == [("refine_out", E), ("refine_groundtruth", E), ("refine_pos_mask", E), ("dtype", torch.float32)]
+    assert params(net_tools.det_clf_loss, 8) == [("refine_out", E), ("clf_out", E), ("det_out", E), ("det_groundtruth", E), ("det_pos_mask", E), ("det_labels", E), ("iou_all_layers", E), ("dtype", torch.float32)]
 
 
 @pytest.mark.parametrize("layout", ["418", "512", "tiny"])
