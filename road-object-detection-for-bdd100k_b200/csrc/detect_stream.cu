@@ -476,7 +476,7 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   float* s_area = reinterpret_cast<float*>(s_nbox + k);
   float* s_score = s_area + k;
   int* s_selected = reinterpret_cast<int*>(s_score + k);
-  __shared__ unsigned long long s_dead, s_sel;
+  __shared__ unsigned long long s_deadw[kSegWarps], s_sel;      // per-warp "suppressed by the kept list" masks of a batch
   __shared__ int s_nsel;
 
   const long long r = blockIdx.x;
@@ -674,7 +674,6 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     // (rare) re-read box and area
     const float4 q0 = c0 < m ? s_qbox[c0] : none;
     const float4 q1 = v1 ? s_qbox[c1] : none;
-    if (tid == 0) s_dead = 0ull;
     // -- vs the kept list: warp w takes rows w, w+8, ...  First a branch-free pass that only records
     // which rows intersect the lane's candidates (pipelined broadcast loads + compares), then the
     // IoU test for the recorded rows only (a few per lane).
@@ -735,13 +734,12 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     }
     s_cmw[lane * kSegWarps + warp] = cm0;
     s_cmw[(lane + 32) * kSegWarps + warp] = cm1;
-    __syncthreads();                                   // s_dead reset + partial masks visible
     {
       const unsigned long long dw = (unsigned long long)__ballot_sync(0xffffffffu, d0) |
                                     ((unsigned long long)__ballot_sync(0xffffffffu, d1) << 32);
-      if (lane == 0 && dw) atomicOr(&s_dead, dw);
+      if (lane == 0) s_deadw[warp] = dw;
     }
-    __syncthreads();
+    __syncthreads();                                   // partial masks of every warp visible
     // -- resolve (warp 0): candidate q is dead if a KEPT earlier candidate suppresses it, kept once no
     // undecided earlier candidate could; every round decides at least the lowest undecided one.
     if (warp == 0) {
@@ -751,7 +749,10 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
         cmA |= (unsigned long long)s_cmw[lane * kSegWarps + w] << (w * (64 / kSegWarps));
         cmB |= (unsigned long long)s_cmw[(lane + 32) * kSegWarps + w] << (w * (64 / kSegWarps));
       }
-      unsigned long long U = ~s_dead;
+      unsigned long long dead = 0ull;
+#pragma unroll
+      for (int w = 0; w < kSegWarps; ++w) dead |= s_deadw[w];
+      unsigned long long U = ~dead;
       if (nb < 64) U &= (1ull << nb) - 1ull;
       unsigned long long K = 0ull;
       while (U) {
