@@ -228,3 +228,23 @@ def test_reshape_list_round_trip():
     assert flat == [img] + a + b
     assert tf_utils.reshape_list(flat, [1, 6, 6]) == [img, a, b]
     assert tf_utils.reshape_list([], None) == [] and tf_utils.reshape_list([1, 2], [1, 1]) == [1, 2]
+
+
+def test_loss_layout_from_lists_and_metric_constants():
+    """Host-side pieces of f-2 / f-3 that need no GPU: the layer layout derived from per-layer head tensors, the VOC07
+    recall levels (np.arange(0., 1.1, 0.1) bit for bit), smooth_l1's formula."""
+    import torch
+    from rodet_b200.utils import losses
+    from rodet_b200.utils.tf_extended import metrics
+    ts = [torch.zeros(2, 4, 4, 6, 11), torch.zeros(2, 2, 2, 9, 11), torch.zeros(2, 1, 1, 9, 11)]
+    sh = losses._Shapes(ts, 11)
+    assert sh.n == 4 * 4 * 6 + 2 * 2 * 9 + 9 and sh.offsets == [0, 96, 132, 141] and sh.n_layers == 3
+    assert sh.layout.n_total == 141 and [sh.layout.offset[i] for i in range(4)] == [0, 96, 132, 141]
+    flat = torch.arange(2 * 141 * 11, dtype=torch.float32).reshape(2, 141, 11)
+    parts = sh.split(flat, 11)
+    assert [tuple(p.shape) for p in parts] == [tuple(t.shape) for t in ts] and parts[1][1, 1, 0, 3, 5] == flat[1, 96 + (1 * 2 + 0) * 9 + 3, 5]
+    with pytest.raises(ValueError):
+        losses._Shapes([torch.zeros(2, 4, 4, 6, 4)], 11)
+    assert np.array_equal(metrics.VOC07_RECALL_LEVELS, np.arange(0., 1.1, 0.1)) and metrics.VOC07_RECALL_LEVELS.size == 11
+    x = torch.tensor([-2.0, -0.5, 0.0, 0.25, 1.0, 3.0])
+    assert torch.allclose(losses.smooth_l1(x), torch.tensor([1.5, 0.125, 0.0, 0.03125, 0.5, 2.5]))
