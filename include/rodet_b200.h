@@ -204,6 +204,11 @@ int rod_bboxes_nms_batch(const float* scores, const float* bboxes, int64_t rows,
  * workspace: rod_detect_workspace_bytes(batch, n_classes, top_k) bytes, 256-aligned. */
 size_t rod_detect_workspace_bytes(const rod_layout_t* layout, int batch, int n_classes,
                                   int top_k);
+/* Diagnostics: byte offset inside the workspace of uint32 flags[n_classes][B] that the last
+ * rod_detect / rod_detect_logits call with select_threshold > 0 left behind: non-zero = the segment
+ * (class, image) was handed to the exact general kernels (candidate list overflow, sampled score cut
+ * too high, massive ties).  The result never depends on it; bench.py reports the rate. */
+size_t rod_detect_flags_offset(const rod_layout_t* layout, int batch, int n_classes, int top_k);
 int rod_detect(const rod_layout_t* layout, const float* anchors_center,
                const rod_layered_t* predictions, const rod_layered_t* localizations,
                const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "rod_bboxes_nms_batch": (_i, [_vp, _vp, _i64, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "rod_bboxes_matching_batch": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "rod_detect_workspace_bytes": (_sz, [_LP, _i, _i, _i]),
+    "rod_detect_flags_offset": (_sz, [_LP, _i, _i, _i]),
     "rod_detect": (_i, [_LP, _vp, _YP, _YP, _YP, _YP, _i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_peak_fp32_nofma": (_i, [_i, _vp, _vp, _vp]),
     "rod_l2_flush": (_i, [_vp, _sz, _vp]),
@@ -156,40 +157,14 @@ class device_guard:
 class LayerList(list):
     """The reference's "list over layers" backed by ONE flat [B, N(, inner)] tensor.
 
-    Behaves like the plain Python list of per-layer tensors the reference returns (the views are
-    created when first touched), and remembers the flat tensor so that our own functions can
-    hand it on without re-deriving six pointers (`refine_groundtruth` -> `det_groundtruth`)."""
+    A real, eagerly filled `list` of the six per-layer views (so `torch.cat(lst, 1)`, `torch.stack`,
+    `lst + other` and every other consumer that reads the list storage directly see the tensors, like
+    the plain list the reference returns), which also remembers the flat tensor so that our own functions
+    can hand it on without re-deriving six pointers (`refine_groundtruth` -> `det_groundtruth`)."""
 
     def __init__(self, flat, table, batched, trailing_one):
-        super().__init__()
+        super().__init__(table.split(flat, batched, trailing_one))
         self.flat, self.table, self.batched, self.trailing_one = flat, table, batched, trailing_one
-        self._ready = False
-
-    def _fill(self):
-        if not self._ready:
-            self._ready = True
-            super().extend(self.table.split(self.flat, self.batched, self.trailing_one))
-
-    def __len__(self):
-        return self.table.n_layers
-
-    def __getitem__(self, i):
-        self._fill()
-        return super().__getitem__(i)
-
-    def __iter__(self):
-        self._fill()
-        return super().__iter__()
-
-    def __repr__(self):
-        self._fill()
-        return super().__repr__()
-
-    def __eq__(self, other):
-        self._fill()
-        return super().__eq__(other)
-
-    __hash__ = None
 
 
 _DT = {torch.float32: (2, 32), torch.int32: (0, 32), torch.int64: (0, 64)}
@@ -199,8 +174,10 @@ def layered_arg(ts, table, inner, dtype, args, batch_box):
     """rod_layered_t for a per-layer list.  Our own LayerList (same table) is described from its
     flat tensor directly; anything else goes through DLPack and is validated in C."""
     out = Layered()
-    if isinstance(ts, LayerList) and ts.table is table and ts.flat.dtype == dtype and ts.batched:
-        flat = ts.flat
+    if (isinstance(ts, LayerList) and ts.table is table and ts.flat.dtype == dtype and ts.batched and
+            len(ts) == table.n_layers and ts[0].data_ptr() == ts.flat.data_ptr() and
+            ts[-1].data_ptr() == ts.flat.data_ptr() + table.offsets[-2] * inner * ts.flat.element_size()):
+        flat = ts.flat                                 # (still the views it was built with: the list is mutable)
         esz = flat.element_size()
         base, stride = flat.data_ptr(), flat.stride(0)
         for l in range(table.n_layers):

@@ -7,6 +7,7 @@ both float32, 16 B per anchor per table (590 KB at 512x512: L2-resident)."""
 from __future__ import annotations
 
 import ctypes
+import zlib
 
 import numpy as np
 import torch
@@ -96,42 +97,58 @@ class AnchorTable:
         when `batched` is False; `trailing_one` appends a size-1 axis, as the reference does
         for labels and masks)."""
         out = []
+        B, st, off0 = flat.shape[0], flat.stride(), flat.storage_offset()
+        s1 = st[1]
         for l, (fh, fw, a) in enumerate(self.shapes):
-            v = flat[:, self.offsets[l]:self.offsets[l + 1]].unflatten(1, (fh, fw, a))
-            if trailing_one:
-                v = v.unsqueeze(-1)
-            out.append(v if batched else v[0])
+            shape, stride = [B, fh, fw, a], [st[0], fw * a * s1, a * s1, s1]
+            if flat.dim() == 3:
+                shape.append(flat.shape[2]); stride.append(st[2])
+            elif trailing_one:
+                shape.append(1); stride.append(1)
+            if not batched:
+                shape, stride = shape[1:], stride[1:]
+            out.append(flat.as_strided(shape, stride, off0 + self.offsets[l] * s1))
         return out
 
 
 _CACHE = {}
+_CACHE_MAX = 64
+
+
+def _content_key(layers, device, tag):
+    """Cache key from the CONTENT of the anchors (shapes + CRC32 and Adler-32 of the y / x / h / w bytes,
+    ~10 us for the 512x512 layout), so that anchors mutated in place or rebuilt every step never map to a
+    stale table and equal anchors rebuilt by the caller hit the cache."""
+    crc, adl, shapes = 0, 1, []
+    for layer in layers:
+        for v in layer:
+            a = np.ascontiguousarray(v, dtype=np.float32)
+            shapes.append(a.shape)
+            crc = zlib.crc32(a, crc)
+            adl = zlib.adler32(a, adl)
+    return (tag, str(device), tuple(shapes), crc, adl)
+
+
+def _cached(layers, device, tag):
+    key = _content_key(layers, device, tag)
+    t = _CACHE.get(key)
+    if t is None:
+        if len(_CACHE) >= _CACHE_MAX:
+            _CACHE.pop(next(iter(_CACHE)))          # drop the oldest entry only
+        t = _CACHE[key] = AnchorTable.from_anchors(layers, device)
+    return t
 
 
 def table_for(anchors, device):
-    """AnchorTable for an anchors_all_layer() list (cached on the list's identity)."""
+    """AnchorTable for an anchors_all_layer() list, cached on the anchors' content.  Hot loops should
+    build the AnchorTable once and pass it instead of the list (skips the hashing)."""
     if isinstance(anchors, AnchorTable):
         return anchors
-    key = (id(anchors), str(device))
-    hit = _CACHE.get(key)
-    if hit is not None and hit[0] is anchors:
-        return hit[1]
-    if len(_CACHE) > 64:
-        _CACHE.clear()
-    t = AnchorTable.from_anchors(anchors, device)
-    _CACHE[key] = (anchors, t)
-    return t
+    return _cached(anchors, device, "all")
 
 
 def layer_table_for(anchors_one_layer, device):
     """AnchorTable for ONE layer's [y, x, h, w] (what decode/encode_locations_one_layer take)."""
     if isinstance(anchors_one_layer, AnchorTable):
         return anchors_one_layer
-    key = (id(anchors_one_layer), str(device), "1")
-    hit = _CACHE.get(key)
-    if hit is not None and hit[0] is anchors_one_layer:
-        return hit[1]
-    if len(_CACHE) > 64:
-        _CACHE.clear()
-    t = AnchorTable.from_anchors([anchors_one_layer], device)
-    _CACHE[key] = (anchors_one_layer, t)
-    return t
+    return _cached([anchors_one_layer], device, "one")

@@ -188,7 +188,9 @@ clf_pass1_kernel(const __grid_constant__ ClfParams P, const float4* __restrict__
     ce0[o] = __fsub_rn(lse, __fsub_rn(row[0], mx));                       // CE against class 0 (:612)
     if (m_i != 0) {
       nvalues[o] = 1.f;                                                   // tf.where(nmask, p0, 1. - fnmask)
-      const float ce = __fsub_rn(lse, __fsub_rn(row[lab], mx));           // CE against the matched class (:605)
+      // CE against the matched class (:605).  A label outside [0, C) gives NaN, like TF's GPU kernel of
+      // sparse_softmax_cross_entropy_with_logits (its CPU kernel raises), instead of an out-of-bounds read.
+      const float ce = (lab >= 0 && lab < P.C) ? __fsub_rn(lse, __fsub_rn(row[lab], mx)) : __int_as_float(0x7fc00000);
       const float f = iou_factor(P.iou.base[l][(long long)b * P.iou.stride[l] + i], stats[(size_t)b * P.L.n_layers + l]);
       pos_acc += (double)__fmul_rn(ce, f);
       npos += 1;
@@ -342,6 +344,8 @@ clf_grad_kernel(const __grid_constant__ ClfParams P, const float4* __restrict__ 
         const float p = __fmul_rn(softmax_exp(row[c], mx), rinv);
         row[c] = w * (p - (c == target ? 1.f : 0.f));
       }
+      if (target < 0 || target >= P.C)                   // invalid label: NaN row, as the forward loss
+        for (int c = 0; c < P.C; ++c) row[c] = __int_as_float(0x7fc00000);
     }
   }
   __syncthreads();
@@ -420,6 +424,7 @@ static int clf_params(const rod_layout_t* layout, const rod_layered_t* logits, c
       (rc = check_layered(mask, nl, "mask")) || (rc = check_layered(iou, nl, "iou")))
     return rc;
   ROD_REQUIRE(batch >= 1 && n_classes >= 1 && n_classes <= ROD_MAX_CLASSES, "rod_clf_loss: batch=%d n_classes=%d invalid", batch, n_classes);
+  ROD_REQUIRE(batch <= 65535, "rod_clf_loss: batch=%d exceeds 65535 (grid y dimension)", batch);
   P->L = to_layout(layout);
   P->logits = to_layered_f(logits, nl); P->iou = to_layered_f(iou, nl);
   P->labels = to_layered_i(labels, nl); P->mask = to_layered_i(mask, nl);

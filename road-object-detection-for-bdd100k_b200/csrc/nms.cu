@@ -258,6 +258,13 @@ extern "C" size_t rod_detect_workspace_bytes(const rod_layout_t* layout, int bat
   return ((per * 4 + 255) / 256) * 256 * 2 + 256 + rod::stream_workspace_bytes(batch, n_classes, top_k);
 }
 
+extern "C" size_t rod_detect_flags_offset(const rod_layout_t* layout, int batch, int n_classes, int top_k) {
+  (void)layout;
+  if (batch <= 0 || n_classes <= 0 || top_k <= 0) return 0;
+  const size_t per = (size_t)batch * n_classes * top_k;
+  return ((per * 4 + 255) / 256) * 256 * 2;       // the streaming workspace starts with the flags (launch_detect_stream)
+}
+
 namespace rod {
 static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
                           const rod_layered_t* predictions, const rod_layered_t* localizations,
@@ -279,6 +286,7 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   }
   ROD_REQUIRE(out_scores && out_bboxes && workspace, "rod_detect: NULL output / workspace");
   ROD_REQUIRE(batch >= 0 && n_classes >= 1 && n_classes <= ROD_MAX_CLASSES, "rod_detect: batch=%d n_classes=%d invalid", batch, n_classes);
+  ROD_REQUIRE(batch <= 65535, "rod_detect: batch=%d exceeds 65535 (grid y dimension)", batch);
   ROD_REQUIRE(keep_top_k >= 1, "rod_detect: keep_top_k=%d invalid", keep_top_k);
   ROD_REQUIRE(top_k >= 1 && top_k <= layout->n_total, "rod_detect: top_k=%d must be in [1, N=%d] (tf.nn.top_k requires k <= N)", top_k, layout->n_total);
   if (top_k > ROD_MAX_TOPK) {

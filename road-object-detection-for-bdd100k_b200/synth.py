@@ -71,3 +71,53 @@ def stress_probs(image_index: int, n_anchors: int, thr: float = 0.3, n_cols: int
     """NMS stress (BASELINE config 5): every (anchor, class) score ~ U(thr, 1)."""
     rng = np.random.default_rng([BASE_SEED + int(image_index), 1299709])
     return rng.uniform(thr, 1.0, size=(n_anchors, n_cols)).astype(np.float32)
+
+
+def _layer_grid(shapes):
+    """Per flat anchor (layer-major, (fy, fx, a) row-major): layer, cell-centre y, x in [0,1]."""
+    lay, ys, xs = [], [], []
+    for l, (fh, fw, a) in enumerate(shapes):
+        fy, fx, _ = np.meshgrid(np.arange(fh), np.arange(fw), np.arange(a), indexing="ij")
+        lay.append(np.full(fh * fw * a, l, dtype=np.int32))
+        ys.append(((fy.reshape(-1) + 0.5) / fh).astype(np.float32))
+        xs.append(((fx.reshape(-1) + 0.5) / fw).astype(np.float32))
+    return np.concatenate(lay), np.concatenate(ys), np.concatenate(xs)
+
+
+_GRID_CACHE = {}
+
+
+def clustered_probs(image_index: int, shapes, mode: str = "quadrant", thr: float = 0.3, n_cols: int = 11):
+    """Spatially CLUSTERED class scores [N,11] f32 (what a trained head produces, unlike the i.i.d. generators
+    above): `shapes` is the per-layer (fh, fw, A) list of the anchor layout.
+
+      quadrant : the candidates (score >= thr) of class c all lie in ONE image quadrant of ONE of the three
+                 finest layers, where about half of the anchors score U(thr, 1); everything else is U(0, thr/2).
+      bumps    : a Gaussian bump of class `label` around every synthetic GT box of the image
+                 (gt_boxes(image_index)), peak U(0.7, 1), width tied to the box size, on every layer;
+                 background noise U(0, thr/2).  Hundreds of candidates per class packed around a few centres."""
+    key = tuple(tuple(int(v) for v in s) for s in shapes)
+    if key not in _GRID_CACHE:
+        _GRID_CACHE[key] = _layer_grid(key)
+    lay, ys, xs = _GRID_CACHE[key]
+    n = lay.shape[0]
+    rng = np.random.default_rng([BASE_SEED + int(image_index), 15485863, 0 if mode == "quadrant" else 1])
+    p = rng.uniform(0.0, thr / 2, size=(n, n_cols)).astype(np.float32)
+    if mode == "quadrant":
+        for c in range(1, n_cols):
+            l = int(rng.integers(0, min(3, len(key))))
+            qy, qx = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+            inside = (lay == l) & ((ys >= 0.5) == bool(qy)) & ((xs >= 0.5) == bool(qx))
+            hit = inside & (rng.random(n) < 0.5)
+            p[hit, c] = rng.uniform(thr, 1.0, size=int(hit.sum())).astype(np.float32)
+    elif mode == "bumps":
+        boxes, labels = gt_boxes(image_index)
+        for (ymin, xmin, ymax, xmax), c in zip(boxes, labels):
+            cy, cx, h, w = (ymin + ymax) / 2, (xmin + xmax) / 2, ymax - ymin, xmax - xmin
+            d2 = ((ys - cy) / (0.25 * h + 1e-3)) ** 2 + ((xs - cx) / (0.25 * w + 1e-3)) ** 2
+            bump = (rng.uniform(0.7, 1.0) * np.exp(-0.5 * d2) * rng.uniform(0.85, 1.0, size=n)).astype(np.float32)
+            if int(c) < n_cols:
+                p[:, int(c)] = np.maximum(p[:, int(c)], bump)
+    else:
+        raise ValueError("mode must be 'quadrant' or 'bumps'")
+    return p

@@ -6,10 +6,16 @@ det_groundtruth, as CUDA kernels behind torch.autograd.Function (csrc/loss.cu).
     det_clf_loss(refine_out, clf_out, det_out, det_gt, det_pos_mask, det_labels, iou_all_layers)   :519-623
 
 Values follow the reference within the float tolerance of the north star (1e-5 relative: TF's float32
-reductions and exp / log kernels have their own rounding).  Gradients flow to the head outputs
-(refine_out for refine_loss, det_out and clf_out for det_clf_loss); targets, masks, labels and the IoU
-factor are constants — the reference builds them from refine_out inside the same graph without a
-stop_gradient, which lets TF differentiate through the target assignment; that path is not reproduced."""
+reductions and exp / log kernels have their own rounding).
+
+Gradients.  By default they flow to the head outputs only (refine_out for refine_loss, det_out and clf_out
+for det_clf_loss) and targets, masks, labels and the IoU factor are constants.  The reference graph has no
+stop_gradient between det_groundtruth and the losses, so TF back-propagates two more terms into refine_out:
+  (1) det_loss through det_gt = (offset_gt - refine_out) * mask (utils/net_tools.py:471), a linear term
+      equal to the det_out gradient on the masked anchors — reproduced by
+      `det_clf_loss(..., reference_gradients=True)`;
+  (2) clf_loss through iou_factor (decode -> jaccard -> moments / min / max / pow, :590-600) — NOT reproduced
+      (dropped in both modes); the integer masks and labels carry no gradient in TF either."""
 from __future__ import annotations
 
 import torch
@@ -76,15 +82,19 @@ def _split_like(flat, xs, tail):
 
 
 class _SmoothL1Sum(torch.autograd.Function):
-    """sum(smooth_l1((y - x) * mask)) / bs over all layers; gradient w.r.t. the x layers."""
+    """sum(smooth_l1((y - x) * mask)) / bs over all layers; gradient w.r.t. the x layers.  Tensors after
+    the first n_layers of `xs` are "twins" (reference_gradients: the refine_out layers behind y) that
+    receive the same gradient as the x layer of the same index."""
 
     @staticmethod
     def forward(ctx, y, mask, n_layers, *xs):
+        ctx.n_twins = len(xs) - n_layers
+        xs = xs[:n_layers]
         xs_d = [x.detach() for x in xs]
         dev = xs_d[0].device
         table = _table_of(y if isinstance(y, _abi.LayerList) else xs_d, 4)
         a, bb = _abi.DLArgs(), [-1]
-        need_grad = any(x.requires_grad for x in xs)
+        need_grad = any(ctx.needs_input_grad[3:])
         with _abi.device_guard(dev):
             xa = _abi.layered_arg(_floats(xs_d), table, 4, torch.float32, a, bb)
             ya = _abi.layered_arg(_floats(y), table, 4, torch.float32, a, bb)
@@ -102,7 +112,7 @@ class _SmoothL1Sum(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         if ctx.grad is None:
-            return (None, None, None) + (None,) * len(ctx.shapes)
+            return (None, None, None) + (None,) * (len(ctx.shapes) + ctx.n_twins)
         flat = ctx.grad * g
         outs, off = [], 0
         for s in ctx.shapes:
@@ -111,7 +121,7 @@ class _SmoothL1Sum(torch.autograd.Function):
                 n *= d
             outs.append(flat[:, off:off + n].reshape(s))
             off += n
-        return (None, None, None) + tuple(outs)
+        return (None, None, None) + tuple(outs) + tuple(outs[:ctx.n_twins])
 
 
 class _ClfLoss(torch.autograd.Function):
@@ -168,12 +178,17 @@ def refine_loss(refine_out, refine_groundtruth, refine_pos_mask, dtype=torch.flo
 
 
 def det_clf_loss(refine_out, clf_out, det_out, det_groundtruth, det_pos_mask, det_labels, iou_all_layers,
-                 dtype=torch.float32, return_details=False):
+                 dtype=torch.float32, return_details=False, reference_gradients=False):
     """(det_loss, clf_loss) of utils/net_tools.py:519-623: smooth-L1 on the ODM offsets, and the classification
     loss with hard-negative mining (negatives = the 3 * n_pos + bs anchors with the lowest background
     probability), positives weighted by the normalised IoU to the 4th power, clf_loss = neg_loss / 2 + pos_loss.
-    return_details adds a dict with pos_loss, neg_loss, max_hard_pred, n_pos, n_neg (the reference's summaries)."""
-    det_loss = _SmoothL1Sum.apply(det_groundtruth, det_pos_mask, len(det_out), *list(det_out)).to(dtype)
+    return_details adds a dict with pos_loss, neg_loss, max_hard_pred, n_pos, n_neg (the reference's summaries).
+    reference_gradients=True also sends det_loss's gradient into refine_out, as TF does through
+    det_gt = (offset_gt - refine_out) * mask (see the module docstring; the IoU-factor path stays dropped)."""
+    twins = list(refine_out) if reference_gradients else []
+    if twins and len(twins) != len(det_out):
+        raise ValueError("refine_out and det_out do not have the same number of layers")
+    det_loss = _SmoothL1Sum.apply(det_groundtruth, det_pos_mask, len(det_out), *(list(det_out) + twins)).to(dtype)
     clf_loss, aux = _ClfLoss.apply(det_labels, det_pos_mask, iou_all_layers, len(clf_out), *list(clf_out))
     clf_loss = clf_loss.to(dtype)
     if return_details:

@@ -27,7 +27,7 @@ __all__ = [
     "init_anchor", "n_anchor_each_layer", "anchors_one_layer", "anchors_all_layer",
     "encode_locations_one_layer", "decode_locations_one_layer", "jaccard", "refine_groundtruth",
     "det_groundtruth", "bboxes_select_one_layer", "bboxes_select_all_layers", "detected_bboxes",
-    "decode_detected_bboxes",
+    "decode_detected_bboxes", "detect_workspace", "detect_fallback_flags", "softmax",
 ]
 
 
@@ -327,8 +327,30 @@ def _select(preds, locs, select_threshold, num_classes, ignore_class):
 
 
 # --------------------------------------------------------------------------------- a15 post-process
+def detect_workspace(anchors_or_n_anchors, batch, top_k, device, num_classes=None):
+    """Extension: a reusable workspace for detected_bboxes / decode_detected_bboxes (`workspace=`), so that a
+    loop does not allocate one per call, and whose fallback flags can be read with detect_fallback_flags()."""
+    C = config.total_obj_n if num_classes is None else int(num_classes)
+    lay = _abi.Layout()
+    if not isinstance(anchors_or_n_anchors, int):
+        lay = table_for(anchors_or_n_anchors, torch.device(device)).layout
+    nbytes = int(_abi.lib.rod_detect_workspace_bytes(lay, int(batch), C, int(top_k)))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+    ws._rod_key = (int(batch), C, int(top_k))
+    return ws
+
+
+def detect_fallback_flags(workspace):
+    """int32 [C, B] view into a detect_workspace(): non-zero where the last call handed the (class, image)
+    segment to the exact general kernels (list overflow, sampled cut too high, massive ties).  Diagnostics
+    only — results never depend on it."""
+    B, C, k = workspace._rod_key
+    off = int(_abi.lib.rod_detect_flags_offset(_abi.Layout(), B, C, k))
+    return workspace[off:off + 4 * B * C].view(torch.int32).view(C, B)
+
+
 def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_threshold, clipping_bbox,
-            top_k, keep_top_k, num_classes, return_counts, from_logits=False):
+            top_k, keep_top_k, num_classes, return_counts, from_logits=False, workspace=None):
     thr = 0.0 if select_threshold is None else float(select_threshold)
     preds = [_f32(p, "predictions") for p in preds]
     dev, B, C = preds[0].device, preds[0].shape[0], preds[0].shape[-1]
@@ -347,7 +369,12 @@ def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_thr
     boxes = torch.empty((C, B, keep_top_k, 4), dtype=torch.float32, device=dev)
     counts = torch.empty((C, B), dtype=torch.int32, device=dev) if return_counts else None
     if B:
-        ws = torch.empty((int(_abi.lib.rod_detect_workspace_bytes(lay, B, C, top_k)),), dtype=torch.uint8, device=dev)
+        need = int(_abi.lib.rod_detect_workspace_bytes(lay, B, C, top_k))
+        ws = workspace
+        if ws is None:
+            ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+        elif ws.dtype != torch.uint8 or ws.numel() < need or ws.device != dev or not ws.is_contiguous():
+            raise ValueError("workspace must be a contiguous uint8 CUDA tensor of >= %d bytes (detect_workspace())" % need)
         clip = None
         if clipping_bbox is not None:
             clip = torch.as_tensor(clipping_bbox, dtype=torch.float32, device=dev).reshape(4).contiguous()
@@ -382,7 +409,8 @@ def softmax(clf_out, out=None):
 
 
 def detected_bboxes(predictions, localisations, select_threshold=None, nms_threshold=0.5,
-                    clipping_bbox=None, top_k=800, keep_top_k=200, return_counts=False, from_logits=False):
+                    clipping_bbox=None, top_k=800, keep_top_k=200, return_counts=False, from_logits=False,
+                    workspace=None):
     """select -> top_k -> per-class NMS -> zero-pad (-> clip) in two kernels
     (utils/net_tools.py:739-758).  predictions: list of [B,fh,fw,A,11] post-softmax scores (or the
     class logits with from_logits=True: slim.softmax is then fused into the select pass);
@@ -390,19 +418,19 @@ def detected_bboxes(predictions, localisations, select_threshold=None, nms_thres
     c -> [B,keep_top_k,4] for c = 1..config.total_obj_n-1."""
     locs = [_f32(l, "localisations") for l in localisations]
     return _detect(list(predictions), locs, None, None, None, select_threshold, nms_threshold,
-                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits)
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits, workspace)
 
 
 def decode_detected_bboxes(anchors_all_layer, refine_out, det_out, predictions, select_threshold=None,
                            nms_threshold=0.5, clipping_bbox=None, top_k=800, keep_top_k=200,
-                           return_counts=False, from_logits=False):
+                           return_counts=False, from_logits=False, workspace=None):
     """Extension: the inference call sequence of evaluate.py:139-151 in one call —
     c2c(decode(anchors, refine_out + det_out)) is evaluated only for the top_k candidates of
     each (image, class) instead of materialising [B,N,4] boxes first."""
     ro = [_f32(t, "refine_out") for t in refine_out]
     do = [_f32(t, "det_out") for t in det_out]
     return _detect(list(predictions), None, ro, do, anchors_all_layer, select_threshold, nms_threshold,
-                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits)
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits, workspace)
 
 
 # --------------------------------------------------------------------------------- f-3 losses

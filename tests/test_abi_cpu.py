@@ -248,3 +248,43 @@ def test_loss_layout_from_lists_and_metric_constants():
     assert np.array_equal(metrics.VOC07_RECALL_LEVELS, np.arange(0., 1.1, 0.1)) and metrics.VOC07_RECALL_LEVELS.size == 11
     x = torch.tensor([-2.0, -0.5, 0.0, 0.25, 1.0, 3.0])
     assert torch.allclose(losses.smooth_l1(x), torch.tensor([1.5, 0.125, 0.0, 0.03125, 0.5, 2.5]))
+
+
+def test_layer_lists_are_real_lists():
+    """The per-layer lists returned by refine_groundtruth / det_groundtruth are consumed by torch.cat / torch.stack /
+    list concatenation, which read the list storage directly (the reference returns plain lists)."""
+    import torch
+    from rodet_b200 import _abi
+    from rodet_b200.anchor_table import AnchorTable
+    shapes = [(3, 2, 6), (2, 2, 9), (1, 1, 9)]
+    n = sum(a * b * c for a, b, c in shapes)
+    table = AnchorTable(shapes, torch.zeros(n, 4), torch.zeros(n, 4))
+    flat4 = torch.arange(2 * n * 4, dtype=torch.float32).view(2, n, 4)
+    flat1 = torch.arange(2 * n, dtype=torch.int32).view(2, n)
+    l4 = _abi.LayerList(flat4, table, True, False)
+    l1 = _abi.LayerList(flat1, table, True, True)
+    assert list.__len__(l4) == 3 and len(l4 + [1]) == 4 and isinstance(l4, list)
+    assert [tuple(t.shape) for t in l4] == [(2, 3, 2, 6, 4), (2, 2, 2, 9, 4), (2, 1, 1, 9, 4)]
+    assert [tuple(t.shape) for t in l1] == [(2, 3, 2, 6, 1), (2, 2, 2, 9, 1), (2, 1, 1, 9, 1)]
+    cat = torch.cat([t.reshape(2, -1, 4) for t in l4], 1)
+    assert torch.equal(cat, flat4)
+    assert torch.equal(torch.cat([t.reshape(2, -1) for t in l1], 1), flat1)
+    assert torch.stack(list(l4[1:2])).shape == (1, 2, 2, 2, 9, 4)
+    assert l4[0].data_ptr() == flat4.data_ptr()                  # zero-copy views
+    one = _abi.LayerList(flat4[:1], table, False, False)          # per-image (reference) form: no batch axis
+    assert [tuple(t.shape) for t in one] == [(3, 2, 6, 4), (2, 2, 9, 4), (1, 1, 9, 4)]
+    idx = _abi.LayerList(flat1, table, True, False)
+    assert [tuple(t.shape) for t in idx] == [(2, 3, 2, 6), (2, 2, 2, 9), (2, 1, 1, 9)]
+    assert torch.equal(idx[1], flat1[:, 36:72].view(2, 2, 2, 9))
+
+
+def test_anchor_cache_key_follows_content():
+    from rodet_b200 import anchor_table
+    import numpy as np
+    a = [[np.zeros((2, 2, 1), np.float32), np.ones((2, 2, 1), np.float32), np.ones(3, np.float32), np.ones(3, np.float32)]]
+    b = [[v.copy() for v in a[0]]]
+    k1, k2 = anchor_table._content_key(a, "cuda:0", "all"), anchor_table._content_key(b, "cuda:0", "all")
+    assert k1 == k2                                               # equal anchors rebuilt by the caller hit the cache
+    b[0][2][1] = 2.0                                              # in-place mutation changes the key
+    assert anchor_table._content_key(b, "cuda:0", "all") != k1
+    assert anchor_table._content_key(a, "cuda:1", "all") != k1 and anchor_table._content_key(a, "cuda:0", "one") != k1

@@ -122,3 +122,55 @@ def test_loss_gradients_vs_torch(env):
             scale = b.grad.abs().max().item()
             assert err <= 2e-6 * max(scale, 1e-6) + 1e-9, (err, scale)
     assert close(cl, ref_cl.item(), 1e-4)
+
+
+def test_reference_gradients_reach_refine_out(env):
+    """reference_gradients=True: det_loss also back-propagates into refine_out through
+    det_gt = (offset_gt - refine_out) * mask (utils/net_tools.py:471; the reference has no stop_gradient), checked
+    against PyTorch autograd on the reference's formula in float64 with det_gt rebuilt from refine_out."""
+    p = _pipeline(env, 4, 7300)
+    B = p["B"]
+    leaf = lambda ts: [t.clone().requires_grad_(True) for t in ts]
+    ro, do = leaf(p["ro"]), leaf(p["do"])
+    dl, _ = env.nt.det_clf_loss(ro, p["clf"], do, p["det_gt"], p["mask"], p["dlab"], p["iou"], reference_gradients=True)
+    dl.backward()
+    ro64 = [t.detach().double().requires_grad_(True) for t in ro]
+    do64 = [t.detach().double().requires_grad_(True) for t in do]
+    ref = 0.0
+    for og, r, d, m in zip(p["gt"], ro64, do64, p["mask"]):
+        mf = m.double()
+        det_gt = (og.double() - r) * mf                       # :471, differentiable w.r.t. refine_out
+        z = (det_gt - d) * mf
+        a = z.abs()
+        ref = ref + (0.5 * ((a - 1) * torch.clamp(a, max=1) + a)).sum() / B
+    ref.backward()
+    n_nonzero = 0
+    for ours, r64 in ((ro, ro64), (do, do64)):
+        for a, b in zip(ours, r64):
+            assert a.grad is not None
+            err = (a.grad.double() - b.grad).abs().max().item()
+            assert err <= 2e-6 * max(b.grad.abs().max().item(), 1e-6) + 1e-9
+            n_nonzero += int((a.grad != 0).sum())
+    assert n_nonzero > 0
+    for r, d in zip(ro, do):
+        assert torch.equal(r.grad, d.grad)
+    # default mode: refine_out receives nothing from det_loss
+    ro2, do2 = leaf(p["ro"]), leaf(p["do"])
+    dl2, _ = env.nt.det_clf_loss(ro2, p["clf"], do2, p["det_gt"], p["mask"], p["dlab"], p["iou"])
+    dl2.backward()
+    assert float(dl2) == float(dl) and all(t.grad is None for t in ro2)
+    assert all(torch.equal(a.grad, b.grad) for a, b in zip(do, do2))
+
+
+def test_invalid_label_gives_nan_not_garbage(env):
+    """A positive anchor with a label outside [0, C): NaN loss / gradient (TF's GPU kernel), never an OOB read."""
+    p = _pipeline(env, 2, 7400)
+    lab = [t.clone() for t in p["dlab"]]
+    mask = [t.clone() for t in p["mask"]]
+    lab[1].view(-1)[5] = 11
+    mask[1].view(-1)[5] = 1
+    clf = [t.clone().requires_grad_(True) for t in p["clf"]]
+    _, cl = env.nt.det_clf_loss(p["ro"], clf, p["do"], p["det_gt"], mask, lab, [t.clone() for t in p["iou"]])
+    assert torch.isnan(cl)
+    cl.backward()
+    assert torch.isnan(clf[1].grad.view(-1, 11)[5]).all() and not torch.isnan(clf[0].grad).any()

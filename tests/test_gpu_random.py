@@ -344,3 +344,82 @@ def test_detect_unrepresentative_sample(env, where):
         assert bit_equal(rb[c].cpu().numpy(), o_b[c]), c
         assert np.array_equal(counts[c].cpu().numpy(), (o_s[c] != 0).sum(1))
     assert (o_s[3] != 0).sum() == B * 200
+
+
+# ------------------------------------------------------------------------------- bench.py's exact launch geometry
+def _detect_vs_c_oracle(env, layout, probs, ro, do, sthr=0.3, nthr=0.45, topk=400, keep=200):
+    """decode_detected_bboxes on the whole batch in ONE launch vs the C oracle (oracle/c, pinned bit-for-bit to
+    oracle/restated.py by tests/test_oracle_c.py), every image, scores and boxes bit-exact.  Returns
+    (#detections, fallback flags [C,B])."""
+    from oracle import c_port as CP
+    table = env.otable[layout]
+    B = probs.shape[0]
+    preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
+    ws = env.nt.detect_workspace(env.anchors[layout], B, topk, env.dev)
+    rs, rb, counts = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=sthr,
+                                                   nms_threshold=nthr, top_k=topk, keep_top_k=keep, return_counts=True,
+                                                   workspace=ws)
+    flags = env.nt.detect_fallback_flags(ws).cpu().numpy()
+    o_s, o_b = CP.detected_bboxes(probs, CP.decode_corner(table, ro, do), sthr, nthr, topk, keep)
+    ndet = 0
+    for c in range(1, 11):
+        g_s, g_b = rs[c].cpu().numpy(), rb[c].cpu().numpy()
+        for b in range(B):
+            assert bit_equal(g_s[b], o_s[c][b]), "scores class %d image %d" % (c, b)
+            assert bit_equal(g_b[b], o_b[c][b]), "boxes class %d image %d" % (c, b)
+        ndet += int((o_s[c] != 0).sum())
+        assert np.array_equal(counts[c].cpu().numpy(), (o_s[c] != 0).sum(1))
+    return ndet, flags
+
+
+@pytest.mark.parametrize("stress", [False, True])
+def test_detect_bench_geometry_bit_exact(env, stress):
+    """BASELINE configs[2] / configs[4] exactly as bench.py launches them: B = 64 images at 512x512 in one call
+    (the scan grid, list-slice size and segment grid all depend on the batch), compared with the oracle image by
+    image."""
+    probs, ro, do = _detect_inputs(env, "512", 500_000, 64, stress)          # bench.py's first decode_nms batch
+    ndet, flags = _detect_vs_c_oracle(env, "512", probs, ro, do)
+    assert ndet > 64 * 100
+    assert flags[1:].mean() < 0.05, "fallback rate on the i.i.d. bench workload: %.3f" % flags[1:].mean()
+
+
+@pytest.mark.parametrize("mode", ["quadrant", "bumps"])
+@pytest.mark.parametrize("B", [64, 3])
+def test_detect_clustered_scores_bit_exact(env, mode, B):
+    """Spatially clustered candidates (a trained head, unlike i.i.d. scores): a class's candidates packed into one
+    quadrant of one layer / around the GT boxes.  Whatever route the segments take (sampled cut, list overflow,
+    exact fallback kernels) the result is the oracle's."""
+    table = env.otable["512"]
+    first = 610_000
+    probs = np.stack([env.synth.clustered_probs(first + b, table.shapes, mode) for b in range(B)])
+    ro = np.stack([env.synth.head_offsets(first + b, table.n, 0, 0.1, 0.2) for b in range(B)])
+    do = np.stack([env.synth.head_offsets(first + b, table.n, 1, 0.1, 0.2) for b in range(B)])
+    ndet, flags = _detect_vs_c_oracle(env, "512", probs, ro, do)
+    assert ndet > B * 50
+    print("clustered %s B=%d: fallback rate %.4f" % (mode, B, flags[1:].mean()))
+
+
+def test_match_encode_bench_geometry_bit_exact(env):
+    """BASELINE configs[1] exactly as bench.py launches it: ARM + ODM on B = 32 images at 512x512 in one launch
+    each, every image compared with the C oracle (masks, indices, labels, matched boxes bit-exact; encodings and
+    IoU bit-exact too: both sides use correctly rounded exp / log)."""
+    from oracle import c_port as CP
+    B, layout = 32, "512"
+    table = env.otable[layout]
+    _, center, labels, counts = _gt_center(env, 0, B)                        # bench.py's first match_encode batch
+    gt, cb, lab, pos, idx = _arm_gpu(env, layout, center, labels, counts)
+    o = CP.arm_match_encode(table, center, labels, counts, R.REFINE_POS_JAC)
+    got = [flat_from_list(x, t) for x, t in ((gt, 1), (cb, 1), (lab, 1), (pos, 1), (idx, 0))]
+    assert np.array_equal(got[3][..., 0], o[3]) and np.array_equal(got[4], o[4])
+    assert np.array_equal(got[2][..., 0], o[2]) and bit_equal(got[1], o[1]) and bit_equal(got[0], o[0])
+    ro = np.stack([env.synth.head_offsets(b, table.n) for b in range(B)])
+    m = o[3] > 0                                                              # half of the positives: a head that has learnt something
+    m[:, 1::2] = False
+    ro[m] = o[0][m] + np.float32(0.05) * ro[m]
+    ro_l = to_cuda_list(ro, table.shapes, (4,), env.dev)
+    det_gt, mask, dlab, iou = env.nt.det_groundtruth(ro_l, gt, cb, lab, pos, env.anchors[layout])
+    d = CP.odm_target(table, ro, o[0], o[1], o[2], o[3], R.DET_POS_JAC)
+    assert np.array_equal(flat_from_list(mask, 1)[..., 0], d[1]) and np.array_equal(flat_from_list(dlab, 1)[..., 0], d[2])
+    assert bit_equal(flat_from_list(iou, 0), d[3]) and bit_equal(flat_from_list(det_gt, 1), d[0])
+    assert int(d[1].sum()) > B * 10
