@@ -150,6 +150,47 @@ extern "C" int rod_dl_odm_target(const rod_layout_t* layout, const DLTensor* anc
                         (float*)dl_ptr(iou), stream);
 }
 
+extern "C" int rod_dl_target_fused(const rod_layout_t* layout, const DLTensor* anchors_corner,
+                                   const DLTensor* anchors_center, const float* arm_thresholds,
+                                   const float* odm_thresholds, const DLTensor* center_bboxes, const DLTensor* labels,
+                                   const DLTensor* gt_counts, const DLTensor* const* refine_out, const DLTensor* gt,
+                                   const DLTensor* cbboxes, const DLTensor* out_labels, const DLTensor* pos_mask,
+                                   const DLTensor* match_idx, const DLTensor* det_gt, const DLTensor* det_mask,
+                                   const DLTensor* det_labels, const DLTensor* iou, void* stream) {
+  int rc = check_layout(layout);
+  if (rc) return rc;
+  const int64_t N = layout->n_total;
+  if ((rc = dl_flat(anchors_corner, "anchors_corner", ROD_kDLFloat, 32, N * 4))) return rc;
+  if ((rc = dl_flat(anchors_center, "anchors_center", ROD_kDLFloat, 32, N * 4))) return rc;
+  if ((rc = dl_check(center_bboxes, "center_bboxes", ROD_kDLFloat, 32))) return rc;
+  DL_REQUIRE(center_bboxes->ndim == 3 && center_bboxes->shape[2] == 4 && dl_compact(center_bboxes, 0),
+             "center_bboxes: expected contiguous [B, G, 4]");
+  int B = (int)center_bboxes->shape[0];
+  const int G = (int)center_bboxes->shape[1];
+  DL_REQUIRE(labels != nullptr, "labels: DLTensor is NULL");
+  const int i64 = labels->dtype.bits == 64;
+  if ((rc = dl_flat(labels, "labels", ROD_kDLInt, i64 ? 64 : 32, (int64_t)B * G))) return rc;
+  if (gt_counts && (rc = dl_flat(gt_counts, "gt_counts", ROD_kDLInt, 32, B))) return rc;
+  rod_layered_t ro;
+  if ((rc = dl_layered(refine_out, layout, 4, ROD_kDLFloat, 32, &B, "refine_out", &ro))) return rc;
+  if ((rc = dl_flat(gt, "gt", ROD_kDLFloat, 32, (int64_t)B * N * 4))) return rc;
+  if (cbboxes && (rc = dl_flat(cbboxes, "cbboxes", ROD_kDLFloat, 32, (int64_t)B * N * 4))) return rc;
+  if (out_labels && (rc = dl_flat(out_labels, "out_labels", ROD_kDLInt, 32, (int64_t)B * N))) return rc;
+  if ((rc = dl_flat(pos_mask, "pos_mask", ROD_kDLInt, 32, (int64_t)B * N))) return rc;
+  if (match_idx && (rc = dl_flat(match_idx, "match_idx", ROD_kDLInt, 32, (int64_t)B * N))) return rc;
+  if ((rc = dl_flat(det_gt, "det_gt", ROD_kDLFloat, 32, (int64_t)B * N * 4))) return rc;
+  if ((rc = dl_flat(det_mask, "det_mask", ROD_kDLInt, 32, (int64_t)B * N))) return rc;
+  if ((rc = dl_flat(det_labels, "det_labels", ROD_kDLInt, 32, (int64_t)B * N))) return rc;
+  if ((rc = dl_flat(iou, "iou", ROD_kDLFloat, 32, (int64_t)B * N))) return rc;
+  return rod_target_fused(layout, (const float*)dl_ptr(anchors_corner), (const float*)dl_ptr(anchors_center),
+                          arm_thresholds, odm_thresholds, (const float*)dl_ptr(center_bboxes), dl_ptr(labels), i64,
+                          gt_counts ? (const int32_t*)dl_ptr(gt_counts) : nullptr, B, G, &ro, (float*)dl_ptr(gt),
+                          cbboxes ? (float*)dl_ptr(cbboxes) : nullptr, out_labels ? (int32_t*)dl_ptr(out_labels) : nullptr,
+                          (int32_t*)dl_ptr(pos_mask), match_idx ? (int32_t*)dl_ptr(match_idx) : nullptr,
+                          (float*)dl_ptr(det_gt), (int32_t*)dl_ptr(det_mask), (int32_t*)dl_ptr(det_labels),
+                          (float*)dl_ptr(iou), stream);
+}
+
 extern "C" int rod_dl_decode(const rod_layout_t* layout, const DLTensor* anchors_center,
                              const DLTensor* const* refine_out, const DLTensor* const* det_out, int to_corner,
                              const DLTensor* out, void* stream) {

@@ -334,7 +334,9 @@ clf_grad_kernel(const __grid_constant__ ClfParams P, const float4* __restrict__ 
       w = 0.5f * scale;
     }
     float* row = s_tile + threadIdx.x * P.C;             // gradient overwrites the logits in place
-    if (w == 0.f) {
+    if (target < 0 || target >= P.C) {                   // invalid label: NaN row, as the forward loss (NaN * 0 = NaN)
+      for (int c = 0; c < P.C; ++c) row[c] = __int_as_float(0x7fc00000);
+    } else if (w == 0.f) {
       for (int c = 0; c < P.C; ++c) row[c] = 0.f;
     } else {
       float mx, s;
@@ -344,8 +346,6 @@ clf_grad_kernel(const __grid_constant__ ClfParams P, const float4* __restrict__ 
         const float p = __fmul_rn(softmax_exp(row[c], mx), rinv);
         row[c] = w * (p - (c == target ? 1.f : 0.f));
       }
-      if (target < 0 || target >= P.C)                   // invalid label: NaN row, as the forward loss
-        for (int c = 0; c < P.C; ++c) row[c] = __int_as_float(0x7fc00000);
     }
   }
   __syncthreads();

@@ -26,7 +26,7 @@ from ..anchor_table import AnchorTable, layer_table_for, table_for
 __all__ = [
     "init_anchor", "n_anchor_each_layer", "anchors_one_layer", "anchors_all_layer",
     "encode_locations_one_layer", "decode_locations_one_layer", "jaccard", "refine_groundtruth",
-    "det_groundtruth", "bboxes_select_one_layer", "bboxes_select_all_layers", "detected_bboxes",
+    "det_groundtruth", "target_gen", "bboxes_select_one_layer", "bboxes_select_all_layers", "detected_bboxes",
     "decode_detected_bboxes", "detect_workspace", "detect_fallback_flags", "softmax",
 ]
 
@@ -262,6 +262,66 @@ def det_groundtruth(refine_out, offset_gt, cbboxes, refine_labels, refine_pos_ma
     LL = _abi.LayerList
     return (LL(det_gt, table, True, False), LL(mask, table, True, True), LL(dlab, table, True, True),
             LL(iou, table, True, False))
+
+
+# --------------------------------------------------------------------------------- a9 + a10 fused
+def target_gen(anchors_all_layer, center_bboxes, labels, refine_out, gt_counts=None,
+               method=None, arm_thresholds=None, det_thresholds=None, return_match_index=False,
+               need_cbboxes=True):
+    """Extension: the training call sequence train.py:109-113 -> :147-149 in ONE kernel —
+    `refine_groundtruth(anchors, center_bboxes, labels, JACCARD_BIGGER)` followed by
+    `det_groundtruth(refine_out, refine_gt, refine_cbboxes, refine_labels, refine_pos_mask, anchors)`.
+    Returns the two result tuples `((refine_gt, refine_cbboxes, refine_labels, refine_pos_mask),
+    (det_gt, det_pos_mask, det_labels, iou_all_layers))`, bit-identical to the two calls; the matched GT,
+    encoding, label and mask never round-trip through HBM (84 instead of 124 bytes per anchor).
+    need_cbboxes=False skips writing refine_cbboxes / refine_labels (only det_groundtruth consumes them):
+    the first tuple then holds None in their place."""
+    JB = config.refine_method.JACCARD_BIGGER
+    if method is not None and method != JB:
+        if method == config.refine_method.JACCARD_TOPK:
+            raise ValueError('Not support now')                   # utils/net_tools.py:424
+        raise ValueError("target_gen fuses the JACCARD_BIGGER branch only; call refine_groundtruth + det_groundtruth")
+    cb = _f32(center_bboxes, "center_bboxes")
+    lab = _abi.require_cuda(labels, "labels")
+    if cb.dim() != 3 or cb.shape[-1] != 4 or lab.shape != cb.shape[:2] or cb.shape[1] < 1:
+        raise ValueError("target_gen takes a batch: center_bboxes [B,Gmax,4] (Gmax >= 1), labels [B,Gmax]")
+    if lab.dtype not in (torch.int64, torch.int32):
+        raise ValueError("labels must be int64 or int32")
+    dev = cb.device
+    table = table_for(anchors_all_layer, dev)
+    ta = _thresholds(config.refine_pos_jac_val_all_layers if arm_thresholds is None else arm_thresholds, table,
+                     "refine_pos_jac_val_all_layers")
+    to = _thresholds(config.det_pos_jac_val_all_layers if det_thresholds is None else det_thresholds, table,
+                     "det_pos_jac_val_all_layers")
+    cb, lab = cb.contiguous(), lab.contiguous()
+    if gt_counts is not None:
+        gt_counts = _abi.require_cuda(gt_counts, "gt_counts").to(torch.int32).contiguous()
+    B, N = cb.shape[0], table.n
+    f32, i32 = torch.float32, torch.int32
+    new = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+    gt, pos = new((B, N, 4), f32), new((B, N), i32)
+    cbo = new((B, N, 4), f32) if need_cbboxes else None
+    lbo = new((B, N), i32) if need_cbboxes else None
+    idx = new((B, N), i32) if return_match_index else None
+    det_gt, mask, dlab, iou = new((B, N, 4), f32), new((B, N), i32), new((B, N), i32), new((B, N), f32)
+    a, bb = _abi.DLArgs(), [B]
+    with _abi.device_guard(dev):
+        ro = _abi.layered_arg(refine_out, table, 4, f32, a, bb)
+        if B:
+            _abi.check(_abi.lib.rod_target_fused(
+                table.layout, table.corner.data_ptr(), table.center.data_ptr(), ta, to, cb.data_ptr(), lab.data_ptr(),
+                1 if lab.dtype == torch.int64 else 0, gt_counts.data_ptr() if gt_counts is not None else None, B,
+                cb.shape[1], ro, gt.data_ptr(), cbo.data_ptr() if cbo is not None else None,
+                lbo.data_ptr() if lbo is not None else None, pos.data_ptr(), idx.data_ptr() if idx is not None else None,
+                det_gt.data_ptr(), mask.data_ptr(), dlab.data_ptr(), iou.data_ptr(), _abi.stream_ptr(dev)))
+    LL = _abi.LayerList
+    arm = (LL(gt, table, True, False), LL(cbo, table, True, False) if need_cbboxes else None,
+           LL(lbo, table, True, True) if need_cbboxes else None, LL(pos, table, True, True))
+    if return_match_index:
+        arm = arm + (LL(idx, table, True, False),)
+    det = (LL(det_gt, table, True, False), LL(mask, table, True, True), LL(dlab, table, True, True),
+           LL(iou, table, True, False))
+    return arm, det
 
 
 # --------------------------------------------------------------------------------- a11 select

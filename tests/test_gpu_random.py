@@ -423,3 +423,38 @@ def test_match_encode_bench_geometry_bit_exact(env):
     assert np.array_equal(flat_from_list(mask, 1)[..., 0], d[1]) and np.array_equal(flat_from_list(dlab, 1)[..., 0], d[2])
     assert bit_equal(flat_from_list(iou, 0), d[3]) and bit_equal(flat_from_list(det_gt, 1), d[0])
     assert int(d[1].sum()) > B * 10
+
+
+@pytest.mark.parametrize("layout,B,first", [("512", 32, 0), ("418", 5, 40), ("512", 1, 77)])
+def test_target_gen_fused_bit_exact(env, layout, B, first):
+    """net_tools.target_gen (ARM + ODM in one kernel, train.py:109-113 -> :147-149) against the C oracle and against
+    the two-call path, every output bit for bit; B = 32 at 512x512 is bench.py's launch."""
+    from oracle import c_port as CP
+    table = env.otable[layout]
+    _, center, labels, counts = _gt_center(env, first, B)
+    o = CP.arm_match_encode(table, center, labels, counts, R.REFINE_POS_JAC)
+    ro = np.stack([env.synth.head_offsets(first + b, table.n) for b in range(B)])
+    m = o[3] > 0
+    m[:, 1::2] = False
+    ro[m] = o[0][m] + np.float32(0.05) * ro[m]
+    d = CP.odm_target(table, ro, o[0], o[1], o[2], o[3], R.DET_POS_JAC)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(env.dev)
+    ro_l = to_cuda_list(ro, table.shapes, (4,), env.dev)
+    arm, det = env.nt.target_gen(env.anchors[layout], t(center), t(labels), ro_l, gt_counts=t(counts), return_match_index=True)
+    got = [flat_from_list(x, k) for x, k in zip(arm, (1, 1, 1, 1, 0))]
+    assert np.array_equal(got[3][..., 0], o[3]) and np.array_equal(got[4], o[4]) and np.array_equal(got[2][..., 0], o[2])
+    assert bit_equal(got[1], o[1]) and bit_equal(got[0], o[0])
+    assert np.array_equal(flat_from_list(det[1], 1)[..., 0], d[1]) and np.array_equal(flat_from_list(det[2], 1)[..., 0], d[2])
+    assert bit_equal(flat_from_list(det[3], 0), d[3]) and bit_equal(flat_from_list(det[0], 1), d[0])
+    assert int(d[1].sum()) > 0
+    # the two-call path gives the same bits; the lists feed the losses / torch.cat like the reference's
+    a2 = env.nt.refine_groundtruth(env.anchors[layout], t(center), t(labels), env.config.refine_method.JACCARD_BIGGER, gt_counts=t(counts))
+    d2 = env.nt.det_groundtruth(ro_l, a2[0], a2[1], a2[2], a2[3], env.anchors[layout])
+    for x, y in zip(arm[:4], a2):
+        assert torch.equal(torch.cat([v.reshape(B, -1) for v in x], 1), torch.cat([v.reshape(B, -1) for v in y], 1))
+    for x, y in zip(det, d2):
+        assert torch.equal(x.flat.view(torch.int32), y.flat.view(torch.int32))
+    # optional outputs skipped
+    arm3, det3 = env.nt.target_gen(env.anchors[layout], t(center), t(labels), ro_l, gt_counts=t(counts), need_cbboxes=False)
+    assert arm3[1] is None and arm3[2] is None and torch.equal(arm3[0].flat, arm[0].flat)
+    assert torch.equal(det3[0].flat.view(torch.int32), det[0].flat.view(torch.int32)) and torch.equal(det3[1].flat, det[1].flat)
