@@ -1,25 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — images/s of the box-level hot path on B200 (BASELINE.json metric).
+"""bench.py — images/s of the box-level hot path on B200 (BASELINE.json metric: match+encode; decode+NMS).
 
-A "step" is one pass of the hot path over one batch of synthetic BDD100K-shaped input
-(512x512 anchor layout, N = 36 852 anchors, 10 classes, <= 100 GT boxes per image):
+A "step" is one pass of the hot path over one batch of synthetic BDD100K-shaped input (512x512 anchor layout,
+N = 36 852 anchors, 10 classes, <= 100 GT boxes per image):
 
-  primary   match_encode  (BASELINE configs[1]): ARM matching + encoding (refine_groundtruth)
-            followed by ODM target generation (det_groundtruth), batch 32 per GPU;
-  secondary decode_nms    (configs[2]): decode + select + top-k 400 + NMS 0.45, batch 64 per GPU;
-            nms_stress    (configs[4]): the same with every (anchor, class) above threshold.
+  match_encode (BASELINE configs[1], primary): training-target generation, ARM matching + encoding followed by ODM
+               target generation (reference: refine_groundtruth -> det_groundtruth, train.py:109-113 -> :147-149) as
+               ONE fused kernel through `net_tools.target_gen`, batch 32 per GPU; the two-call path is timed beside it.
+  decode_nms   (configs[2]): decode + select 0.3 + top-k 400 + NMS 0.45 through `net_tools.decode_detected_bboxes`,
+               batch 64 per GPU; nms_stress (configs[4]): every (anchor, class) above threshold;
+               decode_nms_clustered: spatially clustered candidates, with the rate of segments that fell back to the
+               exact general kernels.
+The default run prints ONE compact JSON line: the contract keys describe match_encode; decode_nms, nms_stress and the
+clustered workload appear as flat `decode_nms_*` / `nms_stress_*` / `decode_nms_clustered_*` scalars.
+`--workload decode_nms` (or nms_stress) makes that workload the primary line instead.
 
-`value` = whole-job images/s with inputs resident in HBM (CUDA events, max over ranks);
-`e2e`   = the same metric through the public Python API with HOST (pinned) buffers, the
-          host->device copies of the inputs and the device->host read of the result inside
-          the timed region;
-`roofline` = algorithmic bytes of the dominant kernel / its measured launch time, against
-          MEASURED_PEAKS.json's HBM copy bandwidth;
-`cpu_baseline` = the CPU oracle (a port of the reference; the reference's own TF-1 path cannot
-          run here) on a bounded sample, rank 0 only.
-Multi-GPU: one process per GPU (torchrun), images sharded by rank, no data-path collective
-for match_encode; decode_nms adds one NCCL all-gather of per-rank detection counts.
-`--impl reference` times the CPU oracle as the reference arm.
+  value        whole-job images/s, inputs resident in HBM, ONE batch in flight (strictly serial steps on one stream);
+               `value_overlapped` = consecutive independent batches alternating over `--streams` streams.
+  timing       K = --steps steps are captured into one CUDA graph (one host launch per K steps) = one timed loop
+               between two CUDA events; loops repeat until >= 50 ms were timed; ms_per_step = median loop / K,
+               max over ranks; `loop_spread` = (min, max) of the per-rank medians and of the loops.
+  roofline     dominant kernel's algorithmic bytes / its launch duration vs MEASURED_PEAKS.json's HBM copy rate; the
+               FP32 non-FMA issue bound of the pair loop is reported next to it (`bound` names the binding one).
+  e2e          the same metric through the public API from pinned HOST buffers: H2D of every input and D2H of the
+               complete result inside the timed region.
+  cpu_baseline the C/OpenMP oracle port (oracle/c) on the host cores, bounded sample (the reference's TF-1 CPU path
+               cannot run: TensorFlow is not installable here).
+  --impl reference   times only that CPU port, in a process that never imports the product package.
+  --global-batch G   strong scaling: G images per step split over the ranks (BASELINE configs[3]: 256).
 """
 from __future__ import annotations
 
@@ -39,24 +47,28 @@ if ROOT not in sys.path:
 
 N_CLASSES = 11
 IMG, FEATS = (512, 512), [(64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (2, 2)]
+SHAPES = [(fh, fw, 6 if i == 0 else 9) for i, (fh, fw) in enumerate(FEATS)]
+N_ANCHORS = sum(a * b * c for a, b, c in SHAPES)
 SELECT_THR, NMS_THR, TOP_K, KEEP = 0.3, 0.45, 400, 200
 FALLBACK_HBM_GBS = 6650.0
+MIN_TIMED_MS = 50.0
 
 
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
-    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="all", choices=["all", "match_encode", "decode_nms", "nms_stress"])
     p.add_argument("--batch", type=int, default=32, help="images per GPU per step, match_encode")
     p.add_argument("--batch-detect", type=int, default=64, help="images per GPU per step, decode_nms")
+    p.add_argument("--global-batch", type=int, default=0, help="strong scaling: images per step over ALL ranks")
     p.add_argument("--no-graphs", action="store_true", help="launch through Python every step instead of CUDA graphs")
-    p.add_argument("--streams", type=int, default=4,
-                   help="CUDA streams that consecutive (independent) batches alternate on; 1 = strictly serial steps")
-    p.add_argument("--skip-secondary", action="store_true")
+    p.add_argument("--streams", type=int, default=4, help="streams of the `value_overlapped` variant")
     p.add_argument("--skip-cpu", action="store_true")
-    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--skip-extras", action="store_true", help="only the primary workload (no flat secondary scalars)")
+    p.add_argument("--cpu-seconds", type=float, default=10.0)
     return p.parse_args()
 
 
@@ -66,11 +78,10 @@ def measured_peaks():
     if os.path.isfile(path):
         try:
             with open(path) as f:
-                d = json.load(f)
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+                return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -97,7 +108,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -112,19 +123,8 @@ class ClockSampler:
             for nm, v in zip(names, parts[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def make_anchors():
-    from rodet_b200 import config
-    from rodet_b200.utils import net_tools
-    config.img_size = IMG
-    sizes = net_tools.init_anchor(len(FEATS))
-    feats = {"layer_%d" % (i + 1): f for i, f in enumerate(FEATS)}
-    anchors = net_tools.anchors_all_layer(IMG, feats, sizes)
-    config.img_size = (418, 418)
-    return anchors
+        busy = [x for x in sm if mx and x >= 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def split_np(flat, shapes, tail):
@@ -136,14 +136,15 @@ def split_np(flat, shapes, tail):
     return out
 
 
-SHAPES = [(fh, fw, 6 if i == 0 else 9) for i, (fh, fw) in enumerate(FEATS)]
-N_ANCHORS = sum(a * b * c for a, b, c in SHAPES)
+def corner_to_center_np(cr):
+    """cornerBboxes_2_centerBboxes (utils/common_tools.py:51-54) on the host, float32 op by op."""
+    cr = np.asarray(cr, dtype=np.float32)
+    return np.stack([(cr[..., 0] + cr[..., 2]) / np.float32(2), (cr[..., 1] + cr[..., 3]) / np.float32(2),
+                     cr[..., 2] - cr[..., 0], cr[..., 3] - cr[..., 1]], -1)
 
 
-def host_inputs_match(first_image, B):
-    """Host (NumPy) inputs of one match_encode step: GT in centre form + ARM head output."""
-    from rodet_b200 import synth
-    from oracle_free_math import corner_to_center_np
+def host_inputs_match(synth, first_image, B):
+    """Host inputs of one match_encode step: GT in centre form (padded), labels, counts, ARM head output."""
     corner, labels, counts = synth.gt_batch(first_image, B)
     center = corner_to_center_np(corner)
     for b in range(B):
@@ -152,578 +153,615 @@ def host_inputs_match(first_image, B):
     return center.astype(np.float32), labels, counts, ro
 
 
-def host_inputs_detect(first_image, B, stress):
-    from rodet_b200 import synth
-    mk = synth.stress_probs if stress else synth.class_probs
-    s = (0.05, 0.05) if stress else (0.1, 0.2)
-    probs = np.stack([mk(first_image + b, N_ANCHORS) for b in range(B)])
+def host_inputs_detect(synth, first_image, B, kind):
+    """kind: normal | stress | quadrant | bumps."""
+    if kind == "stress":
+        probs = np.stack([synth.stress_probs(first_image + b, N_ANCHORS) for b in range(B)])
+    elif kind == "normal":
+        probs = np.stack([synth.class_probs(first_image + b, N_ANCHORS) for b in range(B)])
+    else:
+        probs = np.stack([synth.clustered_probs(first_image + b, SHAPES, kind) for b in range(B)])
+    s = (0.05, 0.05) if kind == "stress" else (0.1, 0.2)
     ro = np.stack([synth.head_offsets(first_image + b, N_ANCHORS, 0, *s) for b in range(B)])
     do = np.stack([synth.head_offsets(first_image + b, N_ANCHORS, 1, *s) for b in range(B)])
     return probs, ro, do
 
 
-# ----------------------------------------------------------------------------------------- reference arm / CPU baseline
-# The reference's own TF-1 CPU path cannot run (TensorFlow is not installable here), so the CPU side
-# is the oracle port: oracle/c (plain C, OpenMP over all host threads), pinned bit-for-bit to
-# oracle/restated.py and through it to the fixtures produced by the unmodified reference.
-def cpu_match_encode(table, center, labels, counts, ro):
-    from oracle import c_port as C
-    from oracle import restated as R
-    g = C.arm_match_encode(table, center, labels, counts, R.REFINE_POS_JAC)
-    return C.odm_target(table, ro, g[0], g[1], g[2], g[3], R.DET_POS_JAC)
+# ----------------------------------------------------------------------------------------- CPU side (oracle port)
+# The reference's own TF-1 CPU path cannot run (TensorFlow is not installable here), so the CPU side is the oracle
+# port: oracle/c (plain C, OpenMP over the host threads), pinned bit-for-bit to oracle/restated.py and through it to
+# the fixtures produced by the unmodified reference.  Nothing below imports the product package.
+class CpuPath:
+    def __init__(self):
+        from oracle import c_port, restated, synth
+        self.C, self.R, self.synth = c_port, restated, synth
+        feats = {"layer_%d" % (i + 1): f for i, f in enumerate(FEATS)}
+        self.table = restated.AnchorTable(restated.anchors_all_layer(IMG, feats, restated.init_anchor(len(FEATS), IMG)))
+        assert self.table.n == N_ANCHORS
+
+    def match_encode(self, inp):
+        c, l, k, ro = inp
+        g = self.C.arm_match_encode(self.table, c, l, k, self.R.REFINE_POS_JAC)
+        return self.C.odm_target(self.table, ro, g[0], g[1], g[2], g[3], self.R.DET_POS_JAC)
+
+    def detect(self, inp):
+        p, ro, do = inp
+        return self.C.detected_bboxes(p, self.C.decode_corner(self.table, ro, do), SELECT_THR, NMS_THR, TOP_K, KEEP)
+
+    def time_images(self, fn, make, per, seconds, max_images=4096, n_inputs=3):
+        """images/s of fn over batches of `per` images (a few prebuilt batches, rotated) until `seconds` of CPU
+        time were spent."""
+        inputs = [make(i) for i in range(n_inputs)]
+        fn(inputs[0])                                          # warm (page faults, OpenMP pool)
+        n_img, t_total, i = 0, 0.0, 1
+        while t_total < seconds and n_img < max_images:
+            inp = inputs[i % n_inputs]
+            t0 = time.perf_counter(); fn(inp); t_total += time.perf_counter() - t0
+            n_img += per; i += 1
+        return n_img / t_total, n_img
 
 
-def cpu_detect(table, probs, ro, do):
-    from oracle import c_port as C
-    return C.detected_bboxes(probs, C.decode_corner(table, ro, do), SELECT_THR, NMS_THR, TOP_K, KEEP)
-
-
-def cpu_baseline(workload, seconds):
-    """Times the CPU oracle port on a bounded sample of the same workload (rank 0, N=1)."""
-    from oracle import c_port as C
-    from oracle import restated as R
-    table = R.AnchorTable(make_anchors())
-    per = 8
-    n_img, t_total = 0, 0.0
-    while t_total < seconds and n_img < 512:
-        if workload == "match_encode":
-            c, l, k, ro = host_inputs_match(900_000 + n_img, per)
-            t0 = time.perf_counter(); cpu_match_encode(table, c, l, k, ro); t_total += time.perf_counter() - t0
-        else:
-            p, ro, do = host_inputs_detect(900_000 + n_img, per, workload == "nms_stress")
-            t0 = time.perf_counter(); cpu_detect(table, p, ro, do); t_total += time.perf_counter() - t0
-        n_img += per
-    return {"value": n_img / t_total, "unit": "images/s", "cores": C.threads(), "kind": "port",
-            "sample": "%d images of the %s workload in batches of %d, C/OpenMP oracle port (oracle/c) on %d threads; "
-                      "the reference's TF-1 CPU path cannot run here (no TensorFlow)" % (n_img, workload, per, C.threads())}
+def cpu_baselines(args, B_m, B_d):
+    """Rank 0, N = 1: bounded samples of the same workloads on the host cores, plus BASELINE configs[0]
+    (decode + NMS of ONE image) on one thread and on all threads."""
+    cp = CpuPath()
+    threads = os.cpu_count() or 1
+    cp.C.set_threads(threads)
+    t = cp.C.threads()
+    sec = args.cpu_seconds
+    v_m, n_m = cp.time_images(cp.match_encode, lambda i: host_inputs_match(cp.synth, 900_000 + i * B_m, B_m), B_m, sec * 0.4)
+    v_d, n_d = cp.time_images(cp.detect, lambda i: host_inputs_detect(cp.synth, 910_000 + i * B_d, B_d, "normal"), B_d, sec * 0.3)
+    one = lambda i: host_inputs_detect(cp.synth, 920_000 + i, 1, "normal")
+    v_1a, _ = cp.time_images(cp.detect, one, 1, sec * 0.1, 200)
+    cp.C.set_threads(1)
+    v_11, n_11 = cp.time_images(cp.detect, one, 1, sec * 0.1, 200)
+    v_m1, _ = cp.time_images(cp.match_encode, lambda i: host_inputs_match(cp.synth, 930_000 + i, 1), 1, sec * 0.1, 200)
+    cp.C.set_threads(threads)
+    note = "C/OpenMP port of the reference path (oracle/c); TF-1 reference cannot run here"
+    return {
+        "match_encode": {"value": v_m, "unit": "images/s", "cores": t, "kind": "port",
+                         "sample": "%d images in batches of %d on %d threads; %s" % (n_m, B_m, t, note)},
+        "decode_nms": {"value": v_d, "unit": "images/s", "cores": t, "kind": "port",
+                       "sample": "%d images in batches of %d on %d threads; %s" % (n_d, B_d, t, note)},
+        "config0": {"decode_nms_1image_ms_1thread": 1e3 / v_11, "decode_nms_1image_ms_all_threads": 1e3 / v_1a,
+                    "match_encode_1image_ms_1thread": 1e3 / v_m1, "images": n_11},
+    }
 
 
 def run_reference(args):
-    """Reference arm: the CPU oracle port with all host threads, rank 0 only, 8 images per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """Reference arm: the CPU port on all host threads, rank 0 only, the GPU arm's images per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import c_port as C
-    from oracle import restated as R
-    C.set_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1; this arm owns the host
-    table = R.AnchorTable(make_anchors())
-    per_step = 8
-    inputs = [host_inputs_match(800_000 + i * per_step, per_step) for i in range(4)]
-    times = []
-    for i in range(args.warmup + args.steps):
-        c, l, k, ro = inputs[i % len(inputs)]
-        t0 = time.perf_counter()
-        cpu_match_encode(table, c, l, k, ro)
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
-    total = float(np.sum(times))
-    v = per_step * len(times) / total
+    cp = CpuPath()
+    cp.C.set_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1; this arm owns the host
+    t = cp.C.threads()
+    world = max(1, args.gpus)
+    B_m = args.global_batch // world if args.global_batch else args.batch
+    B_d = args.global_batch // world if args.global_batch else args.batch_detect
+
+    def timed(fn, inputs, steps, warmup):
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            fn(inputs[i % len(inputs)])
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+        return float(np.sum(ts)), len(ts)
+
+    # bounded: each step is one batch of the GPU arm's size; cap the step count so the run ends within minutes
+    steps_m = max(3, min(args.steps, 40))
+    steps_d = max(3, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
+    res = {}
+    if args.workload in ("all", "match_encode"):
+        ins = [host_inputs_match(cp.synth, 800_000 + i * B_m, B_m) for i in range(3)]
+        tot, n = timed(cp.match_encode, ins, steps_m, warm)
+        res["match_encode"] = (B_m * n / tot, 1e3 * tot / n, n, B_m)
+    for name, kind in (("decode_nms", "normal"), ("nms_stress", "stress")):
+        if args.workload in ("all", name):
+            ins = [host_inputs_detect(cp.synth, 810_000 + i * B_d, B_d, kind) for i in range(2)]
+            tot, n = timed(cp.detect, ins, steps_d if args.workload != "all" or name == "decode_nms" else max(3, steps_d // 4), warm)
+            res[name] = (B_d * n / tot, 1e3 * tot / n, n, B_d)
+    primary = args.workload if args.workload != "all" else "match_encode"
+    v, ms, n, B = res[primary]
     line = {
-        "impl": "reference", "metric": "images/sec (match+encode)", "value": v, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "match_encode: ARM refine_groundtruth(JACCARD_BIGGER) + ODM det_groundtruth, "
-                               "BASELINE configs[1]", "image": "512x512", "anchors": N_ANCHORS, "max_gt": 100,
-                   "images_per_step": per_step,
-                   "note": "CPU port of the reference path (the TF-1 reference cannot run: no TensorFlow); "
-                           "%d images per step so the run stays bounded" % per_step},
-        "cpu_baseline": {"value": v, "unit": "images/s", "cores": C.threads(), "kind": "port",
-                         "sample": "%d steps x %d images, C/OpenMP oracle port on %d threads" % (len(times), per_step, C.threads())},
+        "impl": "reference", "metric": "images/sec (%s)" % ("match+encode" if primary == "match_encode" else "decode+NMS"),
+        "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": n, "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(primary), "batch_per_gpu": B, "global_batch": B * world, "image": "512x512", "anchors": N_ANCHORS,
+                   "max_gt": 100, "note": "CPU port of the reference path on the host cores; rank 0 only; the "
+                                          "step count is capped (%d) so the run stays bounded" % n},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": t, "kind": "port",
+                         "sample": "%d steps x %d images, C/OpenMP oracle port on %d threads" % (n, B, t)},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    for name, (v2, ms2, n2, B2) in res.items():
+        if name != primary:
+            line["%s_value" % name] = v2
+            line["%s_e2e_value" % name] = v2
+            line["%s_ms_per_step" % name] = ms2
+            line["%s_batch_per_gpu" % name] = B2
     print(json.dumps(line), flush=True)
 
 
+def workload_name(w):
+    return {"match_encode": "match_encode: ARM refine_groundtruth(JACCARD_BIGGER) + ODM det_groundtruth, BASELINE configs[1]",
+            "decode_nms": "decode_nms: decode + select %.2f + top-k %d + NMS %.2f keep %d, BASELINE configs[2]" % (SELECT_THR, TOP_K, NMS_THR, KEEP),
+            "nms_stress": "nms_stress: decode_nms with every (anchor, class) above threshold, BASELINE configs[4]"}[w]
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
-def main():
-    args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+class Gpu:
+    """Device, process group and the timing discipline shared by the workloads."""
 
-    import torch
-    import torch.distributed as dist
-    from rodet_b200 import _abi, config
-    from rodet_b200.anchor_table import AnchorTable
-    from rodet_b200.utils import net_tools
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.bind_cores()
+        self.dev = torch.device("cuda", self.local)
+        torch.cuda.set_device(self.dev)
+        if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's banner must not land on stdout (one JSON line)
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.launches = 0
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not land on stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
-    JB = config.refine_method.JACCARD_BIGGER
-    anchors = make_anchors()
-    table = AnchorTable.from_anchors(anchors, dev)
-    hbm_gbs, peak_src = measured_peaks()
-    N = table.n
-    stream = torch.cuda.current_stream(dev)
+    def bind_cores(self):
+        """One disjoint slice of the host cores per rank, before any pinned buffer is allocated (first touch):
+        eight ranks' staging copies otherwise migrate over the same cores."""
+        self.cores = None
+        lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        if lw <= 1 or not hasattr(os, "sched_setaffinity"):
+            return
+        try:
+            avail = sorted(os.sched_getaffinity(0))
+            per = len(avail) // lw
+            if per >= 1:
+                mine = avail[self.local * per:(self.local + 1) * per]
+                os.sched_setaffinity(0, mine)
+                self.cores = [mine[0], mine[-1]]
+        except OSError:
+            pass
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def gather(self, x):
+        """values of x on every rank."""
+        if self.world == 1:
+            return [float(x)]
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
-    side_streams = [torch.cuda.Stream(dev) for _ in range(max(1, args.streams))]
-
-    def time_loop(step_fn, steps, warmup, n_streams=1):
-        """K steps between two CUDA events on the launching stream.  With n_streams > 1 consecutive
-        steps (independent batches, disjoint buffers) alternate over that many streams, all forked
-        from / joined to the timing stream, so a batch's memory-bound kernels overlap the next
-        batch's issue-bound ones."""
-        lanes = side_streams[:n_streams] if n_streams > 1 else [stream]
-
-        def run(first, count):
-            if n_streams > 1:
-                fork = torch.cuda.Event()
-                fork.record(stream)
+    def capture(self, step_fn, K, n_streams=1):
+        """One CUDA graph holding K consecutive steps (one host launch per K steps); with n_streams > 1 the
+        steps alternate over that many forked / joined streams inside the graph."""
+        torch = self.torch
+        if self.args.no_graphs:
+            return None
+        step_fn(0)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        lanes = [torch.cuda.Stream(self.dev) for _ in range(n_streams)] if n_streams > 1 else None
+        with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream(self.dev)
+            if lanes:
                 for s in lanes:
-                    s.wait_event(fork)
-            for i in range(count):
-                with torch.cuda.stream(lanes[i % len(lanes)]):
-                    step_fn(first + i)
-            if n_streams > 1:
+                    s.wait_stream(cur)
+                for i in range(K):
+                    with torch.cuda.stream(lanes[i % n_streams]):
+                        step_fn(i)
                 for s in lanes:
-                    j = torch.cuda.Event()
-                    j.record(s)
-                    stream.wait_event(j)
-        run(0, warmup)
-        barrier()
+                    cur.wait_stream(s)
+            else:
+                for i in range(K):
+                    step_fn(i)
+        return g
+
+    def timed_primary(self, run_loop, K, after_loop=None):
+        """time_loops for the headline number, with nvidia-smi clocks / throttle reasons sampled meanwhile."""
+        sampler = ClockSampler(self.local)
+        if self.rank == 0:
+            sampler.start()
+            time.sleep(0.05)
+        t = self.time_loops(run_loop, K, after_loop, min_ms=4 * MIN_TIMED_MS)
+        self.clocks = sampler.stop() if self.rank == 0 else None
+        return t
+
+    def time_loops(self, run_loop, K, after_loop=None, min_ms=MIN_TIMED_MS, warm_loops=None, max_loops=400):
+        """run_loop() enqueues K steps.  Warm-up loops, barrier + synchronize, then R >= 5 timed loops (each between
+        its own pair of CUDA events on the launching stream) so that >= min_ms are timed, barrier + synchronize.
+        Returns ms per step from the MAX over ranks of the per-rank median loop, plus the spreads."""
+        torch = self.torch
+        warm_loops = warm_loops if warm_loops is not None else max(1, -(-self.args.warmup // K))
+        for _ in range(warm_loops):
+            run_loop()
+            if after_loop:
+                after_loop()
+        torch.cuda.synchronize(self.dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run(warmup + (warmup % 2), steps)
-        e1.record(stream)
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1))
+        e0.record(self.stream); run_loop(); e1.record(self.stream)
+        if after_loop:
+            after_loop()
+        torch.cuda.synchronize(self.dev)
+        est = max(self.gather(e0.elapsed_time(e1)))
+        R = int(min(max_loops, max(5, np.ceil(min_ms / max(est, 1e-3)))))
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+        self.barrier()
+        for a, b in evs:
+            a.record(self.stream)
+            run_loop()
+            b.record(self.stream)
+            if after_loop:
+                after_loop()
+        self.barrier()
+        ts = [a.elapsed_time(b) for a, b in evs]
+        med = float(np.median(ts))
+        meds = self.gather(med)
+        self.launches = R
+        return {"ms_per_step": max(meds) / K, "loops": R, "steps_per_loop": K, "timed_ms": float(np.sum(ts)),
+                "rank_spread_ms_per_step": [min(meds) / K, max(meds) / K],
+                "loop_spread_ms_per_step": [float(np.min(ts)) / K, float(np.max(ts)) / K]}
 
-    def to_dev_list(flat, tail):
-        return [torch.from_numpy(a).to(dev) for a in split_np(flat, SHAPES, tail)]
 
-    # =================================================================== match_encode (primary)
-    B = args.batch
-    # several independent input/output sets, rotated every step, so the working set of
-    # consecutive steps (~150 MB each: 66 MB read + 80 MB written) exceeds the 126 MB L2
-    n_sets = max(4, 2 * args.streams)
+def bench_match(G, table, B, extras):
+    """match_encode: fused target generation (primary) and the two-call path."""
+    torch = G.torch
+    from rodet_b200 import _abi, config, synth
+    from rodet_b200.utils import net_tools
+    args, dev, N = G.args, G.dev, table.n
+    JB = config.refine_method.JACCARD_BIGGER
+    K = max(1, args.steps)
+    n_sets = 8                    # rotating input / output sets: ~100 MB each (19 MB read + 80 MB written) >> 126 MB L2 together
     sets = []
     for s in range(n_sets):
-        c, l, k, ro = host_inputs_match((rank * n_sets + s) * B, B)
+        c, l, k, ro = host_inputs_match(synth, (G.rank * n_sets + s) * B, B)
         sets.append({"center": torch.from_numpy(c).to(dev), "labels": torch.from_numpy(l).to(dev),
-                     "counts": torch.from_numpy(k).to(dev), "ro": to_dev_list(ro, (4,)), "host": (c, l, k, ro)})
+                     "counts": torch.from_numpy(k).to(dev),
+                     "ro": [torch.from_numpy(a).to(dev) for a in split_np(ro, SHAPES, (4,))],
+                     "out": net_tools.target_buffers(table, B, dev), "mean_g": float(k.mean())})
 
-    def arm(s):
-        return net_tools.refine_groundtruth(table, s["center"], s["labels"], JB, gt_counts=s["counts"])
+    def fused(i):
+        s = sets[i % n_sets]
+        return net_tools.target_gen(table, s["center"], s["labels"], s["ro"], gt_counts=s["counts"], out=s["out"])
 
-    def odm(s, t):
+    def two_call(i):
+        s = sets[i % n_sets]
+        t = net_tools.refine_groundtruth(table, s["center"], s["labels"], JB, gt_counts=s["counts"])
         return net_tools.det_groundtruth(s["ro"], t[0], t[1], t[2], t[3], table)
 
-    for s in sets:                       # persistent outputs per set (also the ODM inputs)
-        s["arm_out"] = arm(s)
-        s["odm_out"] = odm(s, s["arm_out"])
-    torch.cuda.synchronize(dev)
+    def runner(fn, n_streams=1):
+        g = G.capture(fn, K, n_streams)
+        if g is None:
+            return lambda: [fn(i) for i in range(K)]
+        return g.replay
 
-    use_graphs = not args.no_graphs
-    launches_per_step = 2
-    if use_graphs:
-        for s in sets:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                t = arm(s)
-                s["graph_out"] = odm(s, t)
-            s["graph"] = g
-            ga, go = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
-                s["ga_out"] = arm(s)
-            with torch.cuda.graph(go):
-                s["go_out"] = odm(s, s["arm_out"])
-            s["g_arm"], s["g_odm"] = ga, go
-        step_m = lambda i: sets[i % n_sets]["graph"].replay()
-        step_arm = lambda i: sets[i % n_sets]["g_arm"].replay()
-        step_odm = lambda i: sets[i % n_sets]["g_odm"].replay()
-    else:
-        step_m = lambda i: odm(sets[i % n_sets], arm(sets[i % n_sets]))
-        step_arm = lambda i: arm(sets[i % n_sets])
-        step_odm = lambda i: odm(sets[i % n_sets], sets[i % n_sets]["arm_out"])
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms_total = time_loop(step_m, args.steps, args.warmup, args.streams if use_graphs else 1)
-    ms_step = ms_total / args.steps
-    ms_step_serial = time_loop(step_m, args.steps, args.warmup, 1) / args.steps if args.streams > 1 else ms_step
-    value = world * B * args.steps / (ms_total * 1e-3)
-
-    # per-kernel launch times for the roofline (same stream, CUDA events, rotating sets)
-    ms_arm = time_loop(step_arm, args.steps, max(3, args.warmup // 4)) / args.steps
-    ms_odm = time_loop(step_odm, args.steps, max(3, args.warmup // 4)) / args.steps
-    clocks = sampler.stop() if rank == 0 else None      # sampled across the timed region and the per-kernel loops
-    mean_g = float(np.mean([s["host"][2].mean() for s in sets]))
-    bytes_arm = B * (40 * N + 20 * mean_g)                     # SURVEY.md §8d: write 40 N, read 20 G
-    bytes_odm = B * 84 * N                                     # read 56 N + write 28 N
-    dom = "odm_target_kernel" if ms_odm >= ms_arm else "arm_jaccard_bigger_kernel"
-    dom_bytes, dom_ms = (bytes_odm, ms_odm) if ms_odm >= ms_arm else (bytes_arm, ms_arm)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f).get(dom)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                "frac": achieved / hbm_gbs, "traffic": traffic,
-                "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per launch)", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
-                "kernels": {"arm_jaccard_bigger_kernel": {"ms": ms_arm, "GBps": bytes_arm / (ms_arm * 1e-3) / 1e9,
-                                                          "frac": bytes_arm / (ms_arm * 1e-3) / 1e9 / hbm_gbs},
-                            "odm_target_kernel": {"ms": ms_odm, "GBps": bytes_odm / (ms_odm * 1e-3) / 1e9,
-                                                  "frac": bytes_odm / (ms_odm * 1e-3) / 1e9 / hbm_gbs}},
-                "step_frac_of_hbm_roofline": (bytes_arm + bytes_odm) / (ms_step * 1e-3) / 1e9 / hbm_gbs}
-
-    # FP32 (no-FMA) issue-rate probe: the ARM loop's compute roofline denominator
-    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    t1 = G.timed_primary(runner(fused), K)
+    launches = t1["loops"] * K
+    res = {"timing": t1, "ms_per_step": t1["ms_per_step"], "value": G.world * B / (t1["ms_per_step"] * 1e-3),
+           "gpu_launches": launches, "kernels_per_step": ["target_fused_kernel"]}
+    mean_g = float(np.mean([s["mean_g"] for s in sets]))
+    hbm, peak_src = measured_peaks()
+    alg = B * (124 * N + 20 * mean_g)             # SURVEY.md 8d: ARM 40 N + 20 G, ODM 84 N per image
+    real = B * (84 * N + 20 * mean_g)             # what the fused kernel moves: 16 N read + 68 N written
+    # FP32 (no FMA) issue-rate probe: the pair loop's compute bound
     import ctypes
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
     ops = ctypes.c_double(0)
     for _ in range(2):
-        _abi.check(_abi.lib.rod_peak_fp32_nofma(4096, sink.data_ptr(), ctypes.addressof(ops), stream.cuda_stream))
+        _abi.check(_abi.lib.rod_peak_fp32_nofma(4096, sink.data_ptr(), ctypes.addressof(ops), G.stream.cuda_stream))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
-    e0.record(stream)
-    _abi.check(_abi.lib.rod_peak_fp32_nofma(4096, sink.data_ptr(), ctypes.addressof(ops), stream.cuda_stream))
-    e1.record(stream)
+    e0.record(G.stream)
+    _abi.check(_abi.lib.rod_peak_fp32_nofma(4096, sink.data_ptr(), ctypes.addressof(ops), G.stream.cuda_stream))
+    e1.record(G.stream)
     torch.cuda.synchronize(dev)
-    fp32_nofma_tops = ops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
-    roofline["note"] = ("ARM is bound by FP32 non-FMA issue, not HBM: evaluating all 14*N*G pair flops at the measured "
-                        "FADD/FMUL rate would take %.1f us per launch; the step as a whole is graded against HBM "
-                        "(step_frac_of_hbm_roofline)" % (14.0 * N * mean_g * B / (fp32_nofma_tops * 1e12) * 1e6))
-    roofline["fp32_nofma_tops_measured"] = fp32_nofma_tops
-    roofline["arm_pair_flops_frac"] = (14.0 * N * mean_g * B / (ms_arm * 1e-3)) / (fp32_nofma_tops * 1e12)
-
-    # ---- e2e: host (pinned) buffers, H2D of the step's inputs + D2H of the result inside the timed region
-    hs = sets[0]["host"]
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_center, h_labels, h_counts = pin(hs[0]), pin(hs[1]), pin(hs[2])
-    h_ro = [pin(a) for a in split_np(hs[3], SHAPES, (4,))]
-    E2E_LANES = 2        # double buffering: a batch's copies overlap the other lane's kernels / copies
-    lanes_m = []
-    for _ in range(E2E_LANES):
-        lanes_m.append({"center": torch.empty_like(h_center, device=dev), "labels": torch.empty_like(h_labels, device=dev),
-                        "counts": torch.empty_like(h_counts, device=dev),
-                        "ro": [torch.empty_like(x, device=dev) for x in h_ro],
-                        "mask": torch.empty((B, N), dtype=torch.int32).pin_memory(), "evt": None})
-    h2d = sum(x.numel() * x.element_size() for x in [h_center, h_labels, h_counts] + h_ro)
-    d2h = B * N * 4
-
-    def step_e2e(i):
-        L = lanes_m[i % E2E_LANES]
-        if L["evt"] is not None:
-            L["evt"].synchronize()                         # the caller consumes this lane's previous result
-        L["center"].copy_(h_center, non_blocking=True)
-        L["labels"].copy_(h_labels, non_blocking=True)
-        L["counts"].copy_(h_counts, non_blocking=True)
-        for d, h in zip(L["ro"], h_ro):
-            d.copy_(h, non_blocking=True)
-        t = net_tools.refine_groundtruth(table, L["center"], L["labels"], JB, gt_counts=L["counts"])
-        o = net_tools.det_groundtruth(L["ro"], t[0], t[1], t[2], t[3], table)
-        L["mask"].copy_(o[1].flat, non_blocking=True)      # ODM positive mask, flat [B,N]
-        L["evt"] = torch.cuda.Event()
-        L["evt"].record(torch.cuda.current_stream(dev))
-
-    e2e_steps = max(6, min(args.steps, 50))
-    ms_e2e = float(np.median([time_loop(step_e2e, e2e_steps, 4, E2E_LANES) for _ in range(3)]))   # host / PCIe variance
-    e2e = {"value": world * B * e2e_steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps,
-           "api": "net_tools.refine_groundtruth + net_tools.det_groundtruth on pinned host inputs; "
-                  "result read back = ODM positive mask [B,N] int32; two batches in flight (double-buffered "
-                  "device inputs on 2 streams), every batch's H2D + kernels + D2H inside the timed region"}
-
-    line = {
-        "metric": "images/sec (match+encode)", "value": value, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "match_encode: ARM refine_groundtruth(JACCARD_BIGGER) + ODM det_groundtruth, "
-                               "BASELINE configs[1]", "batch_per_gpu": B, "global_batch": B * world,
-                   "image": "512x512", "anchors": N, "max_gt": 100, "mean_gt": mean_g,
-                   "l2": "inputs larger than L2: %d rotating input/output sets (~150 MB each)" % n_sets,
-                   "launch": ("CUDA graph replay; consecutive batches alternate over %d streams" % args.streams)
-                   if use_graphs else "python launches", "ms_per_step_1stream": ms_step_serial,
-                   "parallelism": "image-sharded, no collective"},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-    }
-
-    # =================================================================== decode_nms (secondary)
-    if not args.skip_secondary:
-        for name, stress in (("decode_nms", False), ("nms_stress", True)):
-            line[name] = bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_loop, hbm_gbs, N)
-
-        if world == 1:
-            line["decode_nms_from_logits"] = bench_detect_logits(args, dev, table, to_dev_list, time_loop, hbm_gbs, N)
-            line["targets_and_losses"] = bench_losses(args, dev, table, sets, arm, odm, to_dev_list, time_loop, hbm_gbs, N)
-
-    if rank == 0 and not args.skip_cpu and world == 1:
-        line["cpu_baseline"] = cpu_baseline("match_encode", args.cpu_seconds)
-        if not args.skip_secondary:
-            line["decode_nms"]["cpu_baseline"] = cpu_baseline("decode_nms", args.cpu_seconds)
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    fp32_tops = ops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    t_s = t1["ms_per_step"] * 1e-3
+    pair_flops = 14.0 * N * mean_g * B
+    frac_hbm, frac_fp32 = alg / t_s / 1e9 / hbm, pair_flops / t_s / 1e12 / fp32_tops
+    res["roofline"] = {
+        "bound": "hbm" if alg / (hbm * 1e9) >= pair_flops / (fp32_tops * 1e12) else "fp32_nofma",
+        "kernel": "target_fused_kernel", "achieved": alg / t_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": frac_hbm,
+        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "moved_bytes_per_launch": real,
+        "launch_ms": t1["ms_per_step"], "frac_fp32_nofma": frac_fp32, "fp32_nofma_tops_measured": fp32_tops,
+        "pair_flops_per_launch": pair_flops,
+        "note": "one launch = one step (B images); algorithmic bytes = SURVEY 8d M total (124 N + 20 G per image), the "
+                "fused kernel moves 84 N + 20 G; the all-pairs FP32 bound (14 N G flops, no FMA) binds about equally"}
+    if extras:
+        t4 = G.time_loops(runner(fused, args.streams), K)
+        t2 = G.time_loops(runner(two_call), K)
+        res["value_overlapped"] = G.world * B / (t4["ms_per_step"] * 1e-3)
+        res["ms_per_step_overlapped"] = t4["ms_per_step"]
+        res["two_call_ms_per_step"] = t2["ms_per_step"]
+        res["two_call_value"] = G.world * B / (t2["ms_per_step"] * 1e-3)
+    res["e2e"] = e2e_match(G, table, B, sets[0], extras)
+    res["config"] = {"workload": workload_name("match_encode"), "batch_per_gpu": B, "global_batch": B * G.world,
+                     "image": "512x512", "anchors": N, "max_gt": 100, "mean_gt": mean_g,
+                     "api": "net_tools.target_gen (fused ARM+ODM kernel)",
+                     "l2": "inputs larger than L2: %d rotating input/output sets of ~100 MB" % n_sets,
+                     "launch": "python launches" if args.no_graphs else "CUDA graph of %d serial steps per host launch, one batch in flight" % K,
+                     "parallelism": "image-sharded, no collective"}
+    return res
 
 
-def bench_detect(args, name, stress, dev, rank, world, table, to_dev_list, time_loop, hbm_gbs, N):
-    import torch
-    import torch.distributed as dist
+def e2e_match(G, table, B, s0, extras):
+    """Public API from pinned host buffers: ONE staging copy H2D (head output | GT | labels | counts), the fused
+    kernel, ONE copy D2H of all eight outputs (68 B / anchor); two batches in flight."""
+    torch = G.torch
+    from rodet_b200 import _abi
+    from rodet_b200.utils import net_tools
+    dev, N = G.dev, table.n
+    ro_host = torch.cat([t.reshape(B, -1, 4) for t in s0["ro"]], 1).cpu()
+    parts = [ro_host.numpy().view(np.uint8).reshape(-1), s0["center"].cpu().numpy().view(np.uint8).reshape(-1),
+             s0["labels"].cpu().numpy().view(np.uint8).reshape(-1), s0["counts"].cpu().numpy().view(np.uint8).reshape(-1)]
+    sizes = [p.size for p in parts]
+    h_in = torch.from_numpy(np.concatenate(parts)).pin_memory()
+    gmax = s0["center"].shape[1]
+    lanes = []
+    for _ in range(2):
+        d_in = torch.empty_like(h_in, device=dev)
+        o0, o1, o2, o3 = np.cumsum([0] + sizes)[:4]
+        ro = d_in[o0:o0 + sizes[0]].view(torch.float32).view(B, N, 4)
+        out = net_tools.target_buffers(table, B, dev, flat=True)
+        lanes.append({"d_in": d_in, "ro": _abi.LayerList(ro, table, True, False),
+                      "center": d_in[o1:o1 + sizes[1]].view(torch.float32).view(B, gmax, 4),
+                      "labels": d_in[o2:o2 + sizes[2]].view(torch.int64).view(B, gmax),
+                      "counts": d_in[o3:o3 + sizes[3]].view(torch.int32), "out": out,
+                      "h_out": torch.empty_like(out["_flat"], device="cpu").pin_memory(),
+                      "h_mask": torch.empty((B, N), dtype=torch.int32).pin_memory(), "evt": None})
+
+    def make_step(full):
+        def step(i):
+            L = lanes[i % 2]
+            if L["evt"] is not None:
+                L["evt"].synchronize()                     # the caller consumes this lane's previous result
+            L["d_in"].copy_(h_in, non_blocking=True)
+            net_tools.target_gen(table, L["center"], L["labels"], L["ro"], gt_counts=L["counts"], out=L["out"])
+            if full:
+                L["h_out"].copy_(L["out"]["_flat"], non_blocking=True)
+            else:
+                L["h_mask"].copy_(L["out"]["mask"], non_blocking=True)
+            L["evt"] = torch.cuda.Event()
+            L["evt"].record(torch.cuda.current_stream(dev))
+        return step
+
+    def run(step, K):
+        fork = torch.cuda.Event()
+        fork.record(G.stream)
+        for s in side:
+            s.wait_event(fork)
+        for i in range(K):
+            with torch.cuda.stream(side[i % 2]):
+                step(i)
+        for s in side:
+            j = torch.cuda.Event()
+            j.record(s)
+            G.stream.wait_event(j)
+
+    side = [torch.cuda.Stream(dev) for _ in range(2)]
+    K = 8
+    full = make_step(True)
+    t = G.time_loops(lambda: run(full, K), K, min_ms=60.0, warm_loops=1, max_loops=20)
+    h2d, d2h = int(h_in.numel()), int(lanes[0]["h_out"].numel())
+    res = {"value": G.world * B / (t["ms_per_step"] * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": t["ms_per_step"],
+           "h2d_GBps_per_rank": h2d / (t["ms_per_step"] * 1e-3) / 1e9, "d2h_GBps_per_rank": d2h / (t["ms_per_step"] * 1e-3) / 1e9,
+           "api": "net_tools.target_gen on pinned host inputs (1 H2D copy), all 8 output lists read back (1 D2H copy), 2 batches in flight"}
+    if extras:
+        mask = make_step(False)
+        t2 = G.time_loops(lambda: run(mask, K), K, min_ms=40.0, warm_loops=1, max_loops=20)
+        res["mask_only_value"] = G.world * B / (t2["ms_per_step"] * 1e-3)
+        res["mask_only_d2h_bytes_per_step"] = B * N * 4
+    return res
+
+
+def bench_detect(G, table, B, kind, extras, primary):
+    """decode_nms on `kind` scores.  Multi-GPU: every step's detection counts [11, B] land in a staging buffer
+    inside the graph and ONE NCCL all-gather per loop (K batches) ships them."""
+    torch = G.torch
+    from rodet_b200 import synth
     from rodet_b200.dist import allgather_counts
     from rodet_b200.utils import net_tools
-    B = args.batch_detect
-    n_sets = max(2, args.streams)                   # >= 2 x 180 MB of inputs > 126 MB L2; one set per stream
+    args, dev, N = G.args, G.dev, table.n
+    K = max(1, args.steps if primary else min(args.steps, 32))
+    n_sets = max(3, args.streams) if extras else 3       # >= 3 x 123 MB of inputs > 126 MB L2; one set (and workspace) per overlapped stream
     sets = []
     for s in range(n_sets):
-        p, ro, do = host_inputs_detect(500_000 + (rank * n_sets + s) * B, B, stress)
-        sets.append({"probs": to_dev_list(p, (N_CLASSES,)), "ro": to_dev_list(ro, (4,)), "do": to_dev_list(do, (4,)),
-                     "host": (p, ro, do) if s == 0 else None})
-
-    def run(s):
-        rs, rb, cnt = net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["probs"], select_threshold=SELECT_THR,
-                                                       nms_threshold=NMS_THR, top_k=TOP_K, keep_top_k=KEEP,
-                                                       return_counts=True)
-        return rs, rb, cnt
-
-    for s in sets:
-        s["out"] = run(s)
-    torch.cuda.synchronize(dev)
-    use_graphs = not args.no_graphs
-    if use_graphs:
-        for s in sets:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                s["gout"] = run(s)
-            s["graph"] = g
-
-    pending = [None]
-    ROUNDS = 4                                            # rounds (of n_sets batches) per count all-gather
-    stage = torch.zeros((ROUNDS, N_CLASSES, n_sets * B), dtype=torch.int32, device=dev) if world > 1 else None
+        p, ro, do = host_inputs_detect(synth, 500_000 + (G.rank * n_sets + s) * B, B, kind)
+        sets.append({"p": [torch.from_numpy(a).to(dev) for a in split_np(p, SHAPES, (N_CLASSES,))],
+                     "ro": [torch.from_numpy(a).to(dev) for a in split_np(ro, SHAPES, (4,))],
+                     "do": [torch.from_numpy(a).to(dev) for a in split_np(do, SHAPES, (4,))],
+                     "ws": net_tools.detect_workspace(table, B, TOP_K, dev), "host": (p, ro, do) if s == 0 else None})
+    stage = torch.zeros((K, N_CLASSES, B), dtype=torch.int32, device=dev)
+    kw = dict(select_threshold=SELECT_THR, nms_threshold=NMS_THR, top_k=TOP_K, keep_top_k=KEEP)
 
     def step(i):
         s = sets[i % n_sets]
-        if use_graphs:
-            s["graph"].replay()
-            s["cnt"] = s["gout"][2]
-        else:
-            s["cnt"] = run(s)[2]
-        if world > 1:
-            # One NCCL all-gather of detection counts per ROUNDS * n_sets batches (SURVEY 7.3-7: the counts
-            # only size the evaluation arrays, so the collective is amortised and its result is consumed one
-            # gather later).  Every round's counts are packed into a staging buffer on the device.
-            cur = torch.cuda.current_stream(dev)
-            s["evt"] = torch.cuda.Event()
-            s["evt"].record(cur)
-            if (i + 1) % n_sets == 0:
-                for o in sets:
-                    if o.get("evt") is not None:
-                        cur.wait_event(o["evt"])
-                r = ((i + 1) // n_sets - 1) % ROUNDS
-                torch.cat([o["cnt"] for o in sets], dim=1, out=stage[r])      # [C, n_sets * B]
-                if r == ROUNDS - 1:
-                    if pending[0] is not None:
-                        pending[0].result()
-                    pending[0] = allgather_counts(stage.view(ROUNDS * N_CLASSES, n_sets * B), n_sets * B * world, async_op=True)
+        s["out"] = net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["p"], workspace=s["ws"],
+                                                    counts_out=stage[i % K], **kw)
 
-    steps = max(10, args.steps // 4)
-    ns = args.streams if use_graphs else 1
-    if world > 1:      # establish the NCCL communicator / channels for this message size outside the timed region
+    pending = [None]
+
+    def ship_counts():
+        if G.world > 1:
+            if pending[0] is not None:
+                pending[0].result()                        # consumed one gather later
+            pending[0] = allgather_counts(stage.view(K * N_CLASSES, B), B * G.world, async_op=True)
+
+    def runner(n_streams=1):
+        g = G.capture(step, K, n_streams)
+        if g is None:
+            return lambda: [step(i) for i in range(K)]
+        return g.replay
+
+    if G.world > 1:                                       # communicator / channels for this message size
         for _ in range(2):
-            allgather_counts(stage.view(ROUNDS * N_CLASSES, n_sets * B), n_sets * B * world)
-        torch.cuda.synchronize(dev)
-    wu = max(2 * n_sets, args.warmup // 4)
-    if world > 1:
-        wu = max(wu, 2 * ROUNDS * n_sets)               # two full gather periods before the clock starts
-    ms = time_loop(step, steps, wu, ns)
+            allgather_counts(stage.view(K * N_CLASSES, B), B * G.world)
+    t1 = (G.timed_primary if primary else G.time_loops)(runner(), K, after_loop=ship_counts)
     if pending[0] is not None:
-        pending[0].result()
-        pending[0] = None
-    ms_serial = time_loop(step, steps, wu, 1) if ns > 1 else ms
-    if pending[0] is not None:
-        pending[0].result()
-        pending[0] = None
-    value = world * B * steps / (ms * 1e-3)
-    alg_bytes = B * (76 * N + (N_CLASSES - 1) * KEEP * 20)        # SURVEY.md §8d
-    res = {"metric": "images/sec (decode+NMS)", "value": value, "unit": "images/s", "ms_per_step": ms / steps,
-           "ms_per_step_1stream": ms_serial / steps, "streams": ns,
-           "steps": steps, "batch_per_gpu": B,
-           "config": {"workload": "%s: decode + select %.2f + top-k %d + NMS %.2f keep %d, BASELINE configs[%d]" % (
-               name, SELECT_THR, TOP_K, NMS_THR, KEEP, 4 if stress else 2),
-               "collective": ("one NCCL all_gather of [%d*11, %d*B] int32 detection counts per %d batches, consumed one gather later" % (ROUNDS, n_sets, ROUNDS * n_sets)) if world > 1 else "none (1 GPU)"},
-           "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
-                        "frac": alg_bytes / (ms / steps * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes_per_step": alg_bytes,
-                        "scope": "whole step (scan + segment kernels)"},
-           "gpu_launches": 5 * steps, "kernels_per_step": ["sample_kernel", "scan_kernel", "segment_kernel", "topk_segment_kernel (flagged segments only)", "nms_kernel (flagged segments only)"], "detections_per_image": float(sets[0]["out"][2].sum().item()) / B}
+        pending[0].result(); pending[0] = None
+    flags = float(np.mean([net_tools.detect_fallback_flags(s["ws"])[1:].float().mean().item() for s in sets]))
+    hbm, peak_src = measured_peaks()
+    alg = B * (76 * N + (N_CLASSES - 1) * KEEP * 20)      # SURVEY.md 8d
+    t_s = t1["ms_per_step"] * 1e-3
+    res = {"timing": t1, "ms_per_step": t1["ms_per_step"], "value": G.world * B / t_s, "over_rate": flags,
+           "gpu_launches": 5 * t1["loops"] * K,
+           "kernels_per_step": ["sample_kernel", "scan_kernel", "segment_kernel", "topk_segment_kernel / nms_kernel (flagged segments only)"],
+           "detections_per_image": float(stage[0, 1:].sum().item()) / B,
+           "roofline": {"bound": "hbm", "kernel": "whole step (sample + scan + segment kernels)", "achieved": alg / t_s / 1e9,
+                        "peak": hbm, "unit": "GB/s", "frac": alg / t_s / 1e9 / hbm, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg, "launch_ms": t1["ms_per_step"]},
+           "config": {"workload": workload_name("nms_stress" if kind == "stress" else "decode_nms") + ("" if kind in ("normal", "stress") else " [%s-clustered scores]" % kind),
+                      "batch_per_gpu": B, "global_batch": B * G.world, "image": "512x512", "anchors": N,
+                      "api": "net_tools.decode_detected_bboxes", "l2": "inputs larger than L2: %d rotating sets of 123 MB" % n_sets,
+                      "launch": "python launches" if args.no_graphs else "CUDA graph of %d serial steps per host launch, one batch in flight" % K,
+                      "collective": ("one NCCL all_gather of the [%d x 11, B] int32 detection counts per %d batches" % (K, K)) if G.world > 1 else "none (1 GPU)"}}
+    if extras:
+        t4 = G.time_loops(runner(args.streams), K, after_loop=ship_counts)
+        if pending[0] is not None:
+            pending[0].result(); pending[0] = None
+        res["value_overlapped"] = G.world * B / (t4["ms_per_step"] * 1e-3)
+        res["ms_per_step_overlapped"] = t4["ms_per_step"]
+    if primary or kind == "normal":
+        res["e2e"] = e2e_detect(G, table, B, sets[0]["host"], kw)
+    return res
 
-    # e2e through the public API with pinned host inputs and results read back
-    p, ro, do = sets[0]["host"]
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_p = [pin(a) for a in split_np(p, SHAPES, (N_CLASSES,))]
-    h_ro = [pin(a) for a in split_np(ro, SHAPES, (4,))]
-    h_do = [pin(a) for a in split_np(do, SHAPES, (4,))]
-    lanes_d = []
+
+def e2e_detect(G, table, B, host, kw):
+    torch = G.torch
+    from rodet_b200 import _abi
+    from rodet_b200.utils import net_tools
+    dev, N = G.dev, table.n
+    p, ro, do = host
+    parts = [np.ascontiguousarray(a).view(np.uint8).reshape(-1) for a in (p, ro, do)]
+    sizes = [a.size for a in parts]
+    h_in = torch.from_numpy(np.concatenate(parts)).pin_memory()
+    lanes = []
     for _ in range(2):
-        lanes_d.append({"p": [torch.empty_like(x, device=dev) for x in h_p], "ro": [torch.empty_like(x, device=dev) for x in h_ro],
-                        "do": [torch.empty_like(x, device=dev) for x in h_do],
-                        "s": torch.empty((N_CLASSES, B, KEEP), dtype=torch.float32).pin_memory(),
-                        "b": torch.empty((N_CLASSES, B, KEEP, 4), dtype=torch.float32).pin_memory(), "evt": None})
-    h_s, h_b = lanes_d[0]["s"], lanes_d[0]["b"]
+        d_in = torch.empty_like(h_in, device=dev)
+        v = lambda k, inner: d_in[sum(sizes[:k]):sum(sizes[:k + 1])].view(torch.float32).view(B, N, inner)
+        lanes.append({"d_in": d_in, "p": table.split(v(0, N_CLASSES)), "ro": table.split(v(1, 4)), "do": table.split(v(2, 4)),
+                      "ws": net_tools.detect_workspace(table, B, TOP_K, dev),
+                      "s": torch.empty((N_CLASSES, B, KEEP), dtype=torch.float32).pin_memory(),
+                      "b": torch.empty((N_CLASSES, B, KEEP, 4), dtype=torch.float32).pin_memory(), "evt": None})
+    side = [torch.cuda.Stream(dev) for _ in range(2)]
 
-    def step_e2e(i):
-        L = lanes_d[i % 2]
+    def step(i):
+        L = lanes[i % 2]
         if L["evt"] is not None:
-            L["evt"].synchronize()                         # the caller consumes this lane's previous result
-        for dl, hl in ((L["p"], h_p), (L["ro"], h_ro), (L["do"], h_do)):
-            for d, h in zip(dl, hl):
-                d.copy_(h, non_blocking=True)
-        rs, rb, cnt = net_tools.decode_detected_bboxes(table, L["ro"], L["do"], L["p"], select_threshold=SELECT_THR,
-                                                       nms_threshold=NMS_THR, top_k=TOP_K, keep_top_k=KEEP,
-                                                       return_counts=True)
+            L["evt"].synchronize()
+        L["d_in"].copy_(h_in, non_blocking=True)
+        rs, rb = net_tools.decode_detected_bboxes(table, L["ro"], L["do"], L["p"], workspace=L["ws"], **kw)
         L["s"][1:].copy_(rs[1]._base[1:], non_blocking=True)   # class-major [C,B,keep] buffers behind the dicts
         L["b"][1:].copy_(rb[1]._base[1:], non_blocking=True)
         L["evt"] = torch.cuda.Event()
         L["evt"].record(torch.cuda.current_stream(dev))
 
-    e2e_steps = max(4, min(steps, 10))
-    ms_e = float(np.median([time_loop(step_e2e, e2e_steps, 2, 2) for _ in range(3)]))
-    res["e2e"] = {"value": world * B * e2e_steps / (ms_e * 1e-3), "unit": "images/s", "ms_per_step": ms_e / e2e_steps,
-                  "h2d_bytes_per_step": sum(x.numel() * 4 for x in h_p + h_ro + h_do),
-                  "d2h_bytes_per_step": (h_s[1:].numel() + h_b[1:].numel()) * 4,
-                  "api": "net_tools.decode_detected_bboxes on pinned host inputs; scores+boxes read back; two batches in flight"}
-    return res
+    def run(K):
+        fork = torch.cuda.Event()
+        fork.record(G.stream)
+        for s in side:
+            s.wait_event(fork)
+        for i in range(K):
+            with torch.cuda.stream(side[i % 2]):
+                step(i)
+        for s in side:
+            j = torch.cuda.Event()
+            j.record(s)
+            G.stream.wait_event(j)
+
+    K = 4
+    t = G.time_loops(lambda: run(K), K, min_ms=60.0, warm_loops=1, max_loops=12)
+    h2d = int(h_in.numel())
+    d2h = int((lanes[0]["s"][1:].numel() + lanes[0]["b"][1:].numel()) * 4)
+    return {"value": G.world * B / (t["ms_per_step"] * 1e-3), "unit": "images/s", "ms_per_step": t["ms_per_step"],
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "h2d_GBps_per_rank": h2d / (t["ms_per_step"] * 1e-3) / 1e9,
+            "api": "net_tools.decode_detected_bboxes on pinned host inputs (1 H2D copy); scores + boxes read back; 2 batches in flight"}
 
 
-def bench_losses(args, dev, table, sets, arm, odm, to_dev_list, time_loop, hbm_gbs, N):
-    """the training epilogue ARM + ODM targets -> refine_loss + det_clf_loss (forward), and the
-    same with backward() to the head outputs, on the match_encode batch (B = 32)."""
-    import torch
-    from rodet_b200 import synth
+def flat(line, prefix, r, keys=("value", "ms_per_step", "value_overlapped", "ms_per_step_overlapped", "over_rate")):
+    for k in keys:
+        if k in r:
+            line["%s_%s" % (prefix, k)] = r[k]
+    if "roofline" in r:
+        line["%s_roofline_frac" % prefix] = r["roofline"]["frac"]
+    if "e2e" in r:
+        line["%s_e2e_value" % prefix] = r["e2e"]["value"]
+    if "timing" in r:
+        line["%s_timed_ms" % prefix] = r["timing"]["timed_ms"]
+    if "config" in r:
+        line["%s_batch_per_gpu" % prefix] = r["config"]["batch_per_gpu"]
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    G = Gpu(args)
+    from rodet_b200 import config
+    from rodet_b200.anchor_table import AnchorTable
     from rodet_b200.utils import net_tools
-    B = args.batch
-    s = sets[0]
-    first = 800_000
-    s["do"] = to_dev_list(np.stack([synth.head_offsets(first + b, N_ANCHORS, 1) for b in range(B)]), (4,))
-    s["clf"] = to_dev_list(np.stack([synth.class_logits(first + b, N_ANCHORS) for b in range(B)]), (N_CLASSES,))
+    config.img_size = IMG
+    anchors = net_tools.anchors_all_layer(IMG, {"layer_%d" % (i + 1): f for i, f in enumerate(FEATS)},
+                                          net_tools.init_anchor(len(FEATS)))
+    config.img_size = (418, 418)
+    table = AnchorTable.from_anchors(anchors, G.dev)
+    strong = args.global_batch > 0
+    if strong and args.global_batch % G.world:
+        raise SystemExit("--global-batch must be divisible by the number of ranks")
+    B_m = args.global_batch // G.world if strong else args.batch
+    B_d = args.global_batch // G.world if strong else args.batch_detect
+    extras = not args.skip_extras
+    primary = "match_encode" if args.workload == "all" else args.workload
 
-    def forward(ro, do, clf):
-        t = arm(s)
-        d = net_tools.det_groundtruth(ro, t[0], t[1], t[2], t[3], table)
-        rl = net_tools.refine_loss(ro, t[0], t[3])
-        dl, cl = net_tools.det_clf_loss(ro, clf, do, d[0], d[1], d[2], d[3])
-        return rl + dl + cl
+    if primary == "match_encode":
+        r = bench_match(G, table, B_m, extras)
+        metric = "images/sec (match+encode)"
+    else:
+        r = bench_detect(G, table, B_d, "stress" if primary == "nms_stress" else "normal", extras, True)
+        metric = "images/sec (decode+NMS)"
+    line = {"metric": metric, "value": r["value"], "unit": "images/s", "n_gpus": G.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": r["config"], "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
+            "kernels_per_step": r["kernels_per_step"], "timing": r["timing"], "clocks": getattr(G, "clocks", None)}
+    for k in ("value_overlapped", "ms_per_step_overlapped", "two_call_ms_per_step", "two_call_value", "over_rate", "detections_per_image"):
+        if k in r:
+            line[k] = r[k]
+    if G.cores:
+        line["host_cores_of_rank0"] = G.cores
 
-    def step_fwd(i):
-        with torch.no_grad():
-            s["loss"] = forward(s["ro"], s["do"], s["clf"])
+    if args.workload == "all" and extras:
+        flat(line, "decode_nms", bench_detect(G, table, B_d, "normal", True, False))
+        flat(line, "nms_stress", bench_detect(G, table, B_d, "stress", False, False))
+        flat(line, "decode_nms_clustered", bench_detect(G, table, B_d, "quadrant", False, False))
+        flat(line, "decode_nms_bumps", bench_detect(G, table, B_d, "bumps", False, False))
 
-    leaves = [[t.clone().requires_grad_(True) for t in s[k]] for k in ("ro", "do", "clf")]
-
-    def step_bwd(i):
-        for ts in leaves:
-            for t in ts:
-                t.grad = None
-        forward(*leaves).backward()
-
-    steps = max(10, args.steps // 8)
-    res = {"config": {"workload": "ARM + ODM targets + refine_loss + det_clf_loss (hard-negative mining), B = %d; "
-                                  "forward / forward_backward are eager launches through autograd, forward_graph is a CUDA-graph replay" % B}}
-    variants = [("forward", step_fwd), ("forward_backward", step_bwd)]
-    if not args.no_graphs:
-        step_fwd(0)
-        torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g), torch.no_grad():
-            s["gloss"] = forward(s["ro"], s["do"], s["clf"])
-        variants.append(("forward_graph", lambda i: g.replay()))
-    for name, fn in variants:
-        ms = time_loop(fn, steps, 3, 1)
-        res["ms_per_step_" + name] = ms / steps
-    res.update({"metric": "images/sec (targets + losses, forward)", "value": B / (res["ms_per_step_forward"] * 1e-3), "unit": "images/s",
-                "loss": float(s["loss"]), "batch_per_gpu": B})
-    return res
-
-
-def bench_detect_logits(args, dev, table, to_dev_list, time_loop, hbm_gbs, N):
-    """the decode_nms workload fed with class LOGITS.  Fused = softmax inside the select
-    pass (no probability tensor in HBM); unfused = net_tools.softmax (writes [B,N,11]) + the same detect."""
-    import torch
-    from rodet_b200 import synth
-    from rodet_b200.utils import net_tools
-    B = args.batch_detect
-    n_sets = max(2, args.streams)
-    sets = []
-    for s in range(n_sets):
-        first = 700_000 + s * B
-        z = np.stack([synth.class_logits(first + b, N_ANCHORS) for b in range(B)])
-        ro = np.stack([synth.head_offsets(first + b, N_ANCHORS, 0, 0.1, 0.2) for b in range(B)])
-        do = np.stack([synth.head_offsets(first + b, N_ANCHORS, 1, 0.1, 0.2) for b in range(B)])
-        d = {"z": to_dev_list(z, (N_CLASSES,)), "ro": to_dev_list(ro, (4,)), "do": to_dev_list(do, (4,))}
-        d["p"] = [torch.empty_like(t) for t in d["z"]]
-        sets.append(d)
-    kw = dict(select_threshold=SELECT_THR, nms_threshold=NMS_THR, top_k=TOP_K, keep_top_k=KEEP, return_counts=True)
-
-    def fused(s):
-        return net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["z"], from_logits=True, **kw)
-
-    def unfused(s):
-        net_tools.softmax(s["z"], out=s["p"])
-        return net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["p"], **kw)
-
-    res = {}
-    steps = max(10, args.steps // 4)
-    ns = 1 if args.no_graphs else args.streams
-    for name, fn in (("fused", fused), ("softmax_then_detect", unfused)):
-        for s in sets:
-            s["out_" + name] = fn(s)
-        torch.cuda.synchronize(dev)
-        if not args.no_graphs:
-            for s in sets:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    s["gout_" + name] = fn(s)
-                s["graph_" + name] = g
-        step = (lambda i, name=name: sets[i % n_sets]["graph_" + name].replay()) if not args.no_graphs else \
-               (lambda i, fn=fn: fn(sets[i % n_sets]))
-        ms = time_loop(step, steps, 2 * n_sets, ns)
-        res["ms_per_step_" + name] = ms / steps
-    same = all(torch.equal(s["out_fused"][0][c], s["out_softmax_then_detect"][0][c]) for s in sets for c in range(1, N_CLASSES))
-    alg_bytes = B * (76 * N + (N_CLASSES - 1) * KEEP * 20)
-    ms = res["ms_per_step_fused"]
-    res.update({"metric": "images/sec (softmax+decode+NMS)", "value": B / (ms * 1e-3), "unit": "images/s", "streams": ns,
-                "batch_per_gpu": B, "fused_equals_unfused": bool(same),
-                "config": {"workload": "decode_nms fed with class logits (SURVEY.md section 8 f-1): softmax fused into the select pass"},
-                "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
-                             "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes_per_step": alg_bytes},
-                "gpu_launches": 5 * steps,
-                "detections_per_image": float(sets[0]["out_fused"][2].sum().item()) / B})
-    return res
-
-
-# tiny NumPy helper kept outside oracle/ so the GPU arm never imports the oracle
-class _M:
-    @staticmethod
-    def corner_to_center_np(cr):
-        cr = np.asarray(cr, dtype=np.float32)
-        return np.stack([(cr[..., 0] + cr[..., 2]) / np.float32(2), (cr[..., 1] + cr[..., 3]) / np.float32(2),
-                         cr[..., 2] - cr[..., 0], cr[..., 3] - cr[..., 1]], -1)
-
-
-sys.modules["oracle_free_math"] = _M
+    if G.rank == 0 and not args.skip_cpu and G.world == 1:
+        cb = cpu_baselines(args, B_m, B_d)
+        line["cpu_baseline"] = cb["match_encode" if primary == "match_encode" else "decode_nms"]
+        if primary == "match_encode":
+            line["decode_nms_cpu_value"] = cb["decode_nms"]["value"]
+        else:
+            line["match_encode_cpu_value"] = cb["match_encode"]["value"]
+        line["cpu_config0"] = cb["config0"]
+    if G.rank == 0:
+        print(json.dumps(line), flush=True)
+    if G.world > 1:
+        G.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -126,14 +126,20 @@ int rod_odm_target(const rod_layout_t* layout, const float* anchors_center,
  * ARM head output.  Same inputs as rod_arm_match_encode plus refine_out (per-layer list, inner 4)
  * and the ODM thresholds; the same eight outputs as the two calls, bit for bit.  cbboxes,
  * out_labels and match_idx may be NULL (a training step only consumes gt / pos_mask and the four
- * ODM outputs).  Per anchor: 16 B read + 68 B written instead of 124 B for the two-call path. */
+ * ODM outputs).  Per anchor: 16 B read + 68 B written instead of 124 B for the two-call path.
+ * workspace: rod_target_fused_workspace_bytes() (= 8) bytes of device memory, 8-byte aligned, holding
+ * the work-item counter of the kernel's dynamic tile scheduler: it must be ZERO before the first call
+ * and every call leaves it zero again, so one cudaMemset at allocation time is enough.  Calls that may
+ * run concurrently (different streams) need different workspaces. */
+size_t rod_target_fused_workspace_bytes(void);
 int rod_target_fused(const rod_layout_t* layout, const float* anchors_corner,
                      const float* anchors_center, const float* arm_thresholds,
                      const float* odm_thresholds, const float* center_bboxes, const void* labels,
                      int labels_i64, const int32_t* gt_counts, int batch, int gmax,
                      const rod_layered_t* refine_out, float* gt, float* cbboxes,
                      int32_t* out_labels, int32_t* pos_mask, int32_t* match_idx, float* det_gt,
-                     int32_t* det_mask, int32_t* det_labels, float* iou, void* stream);
+                     int32_t* det_mask, int32_t* det_labels, float* iou, void* workspace,
+                     void* stream);
 
 /* ---- a7 / a17  decode ------------------------------------------------------------
  * Replaces decode_locations_one_layer (utils/net_tools.py:182-234) and the inference
@@ -363,7 +369,8 @@ int rod_dl_target_fused(const rod_layout_t* layout, const struct DLTensor* ancho
                         const struct DLTensor* cbboxes, const struct DLTensor* out_labels,
                         const struct DLTensor* pos_mask, const struct DLTensor* match_idx,
                         const struct DLTensor* det_gt, const struct DLTensor* det_mask,
-                        const struct DLTensor* det_labels, const struct DLTensor* iou, void* stream);
+                        const struct DLTensor* det_labels, const struct DLTensor* iou,
+                        const struct DLTensor* workspace, void* stream);
 int rod_dl_decode(const rod_layout_t* layout, const struct DLTensor* anchors_center,
                   const struct DLTensor* const* refine_out, const struct DLTensor* const* det_out,
                   int to_corner, const struct DLTensor* out, void* stream);

@@ -29,7 +29,10 @@ for i, a in enumerate(sys.argv):
     if a == "--iters":
         ITERS = int(sys.argv[i + 1])
 what = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()] or ["targets", "detect"]
-table = AnchorTable.from_anchors(BN.make_anchors(), dev)
+config.img_size = BN.IMG
+_anchors = net_tools.anchors_all_layer(BN.IMG, {"layer_%d" % (i + 1): f for i, f in enumerate(BN.FEATS)}, net_tools.init_anchor(len(BN.FEATS)))
+config.img_size = (418, 418)
+table = AnchorTable.from_anchors(_anchors, dev)
 N = table.n
 JB = config.refine_method.JACCARD_BIGGER
 
@@ -65,7 +68,7 @@ if "targets" in what:
     B, n_sets = 32, 8
     sets = []
     for s in range(n_sets):
-        c, l, k, ro = BN.host_inputs_match(s * B, B)
+        c, l, k, ro = BN.host_inputs_match(synth, s * B, B)
         sets.append({"center": torch.from_numpy(c).to(dev), "labels": torch.from_numpy(l).to(dev),
                      "counts": torch.from_numpy(k).to(dev), "ro": to_dev_list(ro, (4,))})
     arm = lambda s: net_tools.refine_groundtruth(table, s["center"], s["labels"], JB, gt_counts=s["counts"])
@@ -76,10 +79,12 @@ if "targets" in what:
     res["arm_us"] = time_graphs([capture(lambda s=s: arm(s))[0] for s in sets])
     res["odm_us"] = time_graphs([capture(lambda s=s: odm(s, s["arm_out"]))[0] for s in sets])
     res["arm_odm_us"] = time_graphs([capture(lambda s=s: odm(s, arm(s)))[0] for s in sets])
-    for tpc in (0, 1, 2, 4, 6, 8, 12):
-        _abi.lib.rod_debug_set_fused_tiles(tpc)
-        res["fused_tpc%d_us" % tpc] = time_graphs([capture(lambda s=s: fused(s))[0] for s in sets])
-    _abi.lib.rod_debug_set_fused_tiles(0)
+    for s in sets:
+        s["buf"] = net_tools.target_buffers(table, B, dev)
+    fused_out = lambda s: net_tools.target_gen(table, s["center"], s["labels"], s["ro"], gt_counts=s["counts"], out=s["buf"])
+    res["fused_us"] = time_graphs([capture(lambda s=s: fused_out(s))[0] for s in sets])
+    torch.cuda.synchronize()
+    assert all(int(s["buf"]["_sched"].abs().sum()) == 0 for s in sets), "scheduler counters not reset"
     res["fused_nocb_us"] = time_graphs([capture(lambda s=s: fused(s, False))[0] for s in sets])
     # parity of the fused kernel against the two-call path on every set
     same = True
@@ -91,31 +96,30 @@ if "targets" in what:
             torch.equal(x.flat.view(torch.int32), y.flat.view(torch.int32)) for x, y in zip(d1, d2))
     res["fused_equals_two_calls"] = bool(same)
     bytes_m = B * (124 * N + 20 * 50.5)
-    res["hbm_frac_fused"] = bytes_m / (res["fused_tpc0_us"] * 1e-6) / 1e9 / 6545.6
+    res["hbm_frac_fused"] = bytes_m / (res["fused_us"] * 1e-6) / 1e9 / 6545.6
     res["hbm_frac_arm_odm"] = bytes_m / (res["arm_odm_us"] * 1e-6) / 1e9 / 6545.6
 
 if "detect" in what:
     B, n_sets = 64, 3
     kw = dict(select_threshold=BN.SELECT_THR, nms_threshold=BN.NMS_THR, top_k=BN.TOP_K, keep_top_k=BN.KEEP, return_counts=True)
-    for name in ("normal", "stress", "quadrant", "bumps"):
-        graphs, wss = [], []
+    tag = ""
+    if True:
+      for name in ("normal", "stress", "quadrant", "bumps"):
+        graphs, wss, keep = [], [], []
         for s in range(n_sets):
             first = 500_000 + s * B
-            if name in ("normal", "stress"):
-                p, ro, do = BN.host_inputs_detect(first, B, name == "stress")
-            else:
-                p = np.stack([synth.clustered_probs(first + b, BN.SHAPES, name) for b in range(B)])
-                ro = np.stack([synth.head_offsets(first + b, N, 0, 0.1, 0.2) for b in range(B)])
-                do = np.stack([synth.head_offsets(first + b, N, 1, 0.1, 0.2) for b in range(B)])
+            p, ro, do = BN.host_inputs_detect(synth, first, B, name)
             d = {"p": to_dev_list(p, (11,)), "ro": to_dev_list(ro, (4,)), "do": to_dev_list(do, (4,))}
             ws = net_tools.detect_workspace(table, B, BN.TOP_K, dev)
             g, out = capture(lambda d=d, ws=ws: net_tools.decode_detected_bboxes(table, d["ro"], d["do"], d["p"], workspace=ws, **kw))
             graphs.append(g)
             wss.append(ws)
             d["out"] = out
+            keep.append(d)
         us = time_graphs(graphs, max(20, ITERS // 2), 6)
+        print(name, tag, us, file=sys.stderr, flush=True)
         rate = float(np.mean([net_tools.detect_fallback_flags(w)[1:].float().mean().item() for w in wss]))
-        res["detect_%s_us" % name] = us
-        res["detect_%s_fallback_rate" % name] = rate
-        res["detect_%s_hbm_frac" % name] = B * (76 * N + 10 * BN.KEEP * 20) / (us * 1e-6) / 1e9 / 6545.6
+        res["detect_%s%s_us" % (name, tag)] = us
+        res["detect_%s%s_fallback_rate" % (name, tag)] = rate
+        res["detect_%s%s_hbm_frac" % (name, tag)] = B * (76 * N + 10 * BN.KEEP * 20) / (us * 1e-6) / 1e9 / 6545.6
 print(json.dumps(res, indent=1))

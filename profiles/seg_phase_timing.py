@@ -9,15 +9,18 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from rodet_b200 import _abi  # noqa: E402
+from rodet_b200 import _abi, config, synth  # noqa: E402
 from rodet_b200.anchor_table import AnchorTable  # noqa: E402
 from rodet_b200.utils import net_tools  # noqa: E402
 
-stress = len(sys.argv) > 1 and sys.argv[1] == "stress"
+kind = sys.argv[1] if len(sys.argv) > 1 else "normal"
 dev = torch.device("cuda:0")
-table = AnchorTable.from_anchors(bench.make_anchors(), dev)
+config.img_size = bench.IMG
+anchors = net_tools.anchors_all_layer(bench.IMG, {"layer_%d" % (i + 1): f for i, f in enumerate(bench.FEATS)}, net_tools.init_anchor(6))
+config.img_size = (418, 418)
+table = AnchorTable.from_anchors(anchors, dev)
 B = 64
-p, ro, do = bench.host_inputs_detect(0, B, stress)
+p, ro, do = bench.host_inputs_detect(synth, 500_000, B, kind)
 tl = lambda a, t: [torch.from_numpy(x).to(dev) for x in bench.split_np(a, bench.SHAPES, t)]
 P, RO, DO = tl(p, (11,)), tl(ro, (4,)), tl(do, (4,))
 dbg = torch.zeros((2 * 11 * B, 8), dtype=torch.int64, device=dev)

@@ -42,8 +42,9 @@ SIGNATURES = {
     "rod_anchor_table_from_grid": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_arm_match_encode": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_odm_target": (_i, [_LP, _vp, _vp, _YP, _YP, _YP, _YP, _YP, _i, _vp, _vp, _vp, _vp, _vp]),
-    "rod_target_fused": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _YP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "rod_dl_target_fused": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rod_target_fused_workspace_bytes": (_sz, []),
+    "rod_target_fused": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _YP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rod_dl_target_fused": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_decode": (_i, [_LP, _vp, _YP, _YP, _i, _i, _vp, _vp]),
     "rod_encode_one_box": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "rod_center_to_corner": (_i, [_vp, _vp, _i64, _vp]),

@@ -156,7 +156,8 @@ extern "C" int rod_dl_target_fused(const rod_layout_t* layout, const DLTensor* a
                                    const DLTensor* gt_counts, const DLTensor* const* refine_out, const DLTensor* gt,
                                    const DLTensor* cbboxes, const DLTensor* out_labels, const DLTensor* pos_mask,
                                    const DLTensor* match_idx, const DLTensor* det_gt, const DLTensor* det_mask,
-                                   const DLTensor* det_labels, const DLTensor* iou, void* stream) {
+                                   const DLTensor* det_labels, const DLTensor* iou, const DLTensor* workspace,
+                                   void* stream) {
   int rc = check_layout(layout);
   if (rc) return rc;
   const int64_t N = layout->n_total;
@@ -182,13 +183,14 @@ extern "C" int rod_dl_target_fused(const rod_layout_t* layout, const DLTensor* a
   if ((rc = dl_flat(det_mask, "det_mask", ROD_kDLInt, 32, (int64_t)B * N))) return rc;
   if ((rc = dl_flat(det_labels, "det_labels", ROD_kDLInt, 32, (int64_t)B * N))) return rc;
   if ((rc = dl_flat(iou, "iou", ROD_kDLFloat, 32, (int64_t)B * N))) return rc;
+  if ((rc = dl_flat(workspace, "workspace", ROD_kDLInt, 32, 2))) return rc;
   return rod_target_fused(layout, (const float*)dl_ptr(anchors_corner), (const float*)dl_ptr(anchors_center),
                           arm_thresholds, odm_thresholds, (const float*)dl_ptr(center_bboxes), dl_ptr(labels), i64,
                           gt_counts ? (const int32_t*)dl_ptr(gt_counts) : nullptr, B, G, &ro, (float*)dl_ptr(gt),
                           cbboxes ? (float*)dl_ptr(cbboxes) : nullptr, out_labels ? (int32_t*)dl_ptr(out_labels) : nullptr,
                           (int32_t*)dl_ptr(pos_mask), match_idx ? (int32_t*)dl_ptr(match_idx) : nullptr,
                           (float*)dl_ptr(det_gt), (int32_t*)dl_ptr(det_mask), (int32_t*)dl_ptr(det_labels),
-                          (float*)dl_ptr(iou), stream);
+                          (float*)dl_ptr(iou), dl_ptr(workspace), stream);
 }
 
 extern "C" int rod_dl_decode(const rod_layout_t* layout, const DLTensor* anchors_center,

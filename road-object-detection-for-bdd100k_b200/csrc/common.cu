@@ -1,4 +1,6 @@
 // Error slot, device info and small host helpers of the C ABI.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <string.h>
@@ -17,6 +19,14 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return ROD_E_CUDA;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ROD_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
 }
 
 int sm_count() {

@@ -39,6 +39,26 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// Programmatic dependent launch (PDL): the kernel may be scheduled while its predecessor in the stream is still
+// running (as soon as every CTA of the predecessor has executed pdl_launch_dependents() or exited); it must call
+// pdl_wait() before touching anything the predecessor writes.  Hides the launch latency and the prologue of the
+// short kernels of one rod_detect call; stream capture turns these launches into programmatic graph edges.
+bool pdl_enabled();   // false when the environment sets ROD_NO_PDL=1 (measurement aid)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Per-layer pointer table passed by value to kernels.
 struct LayeredF {
   const float* base[ROD_MAX_LAYERS];
@@ -87,6 +107,9 @@ struct Thresholds {
 // ---------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // layer of flat anchor n (< n_total).  to_layout() pads offset[i] = n_total for i > n_layers, so the
 // unused entries never count.
 __device__ __forceinline__ int layer_of(const Layout& L, int n) {

@@ -5,21 +5,28 @@
 // With thr > 0 every entry the select stage zeroes (score*0, box*0) ranks below every real
 // candidate and is indistinguishable from pad_axis's zero padding in the output, so only the
 // candidates with p >= thr matter.  Per (class, image) segment:
-//   S   sample_kernel   coarse histogram of the candidates of every 8th 256-anchor tile (1/8 of the data).
+//   S   sample_kernel   coarse histogram of the candidates of every 19th ANCHOR (a spatially stratified
+//                       sample: any cluster of candidates — one object, one image quadrant, one layer — is
+//                       sampled at the same rate; 19 is coprime with the 6 / 9 anchor shapes per cell, so
+//                       consecutive samples come from different cells and cycle through all shapes).
 //   A   scan_kernel     ONE pass over the [B,N,C] scores (or logits: <.,true> computes the softmax of each
 //                       anchor in registers first, f-1).  256-anchor tiles are staged into shared memory
 //                       with TMA bulk copies (cp.async.bulk + mbarrier, double buffered); one thread per
-//                       anchor.  Every CTA derives, per class, a score cut from the sampled histogram such
-//                       that about 2 * top_k candidates of the segment lie above it, and appends the
-//                       candidates above max(thr, cut) to its private slice of the segment's list.
+//                       anchor.  Every CTA derives, per class, TWO score cuts from the sampled histogram:
+//                       about 1.6 * top_k candidates of the segment lie above cut_hi, about 4 * top_k above
+//                       cut_lo.  Candidates >= cut_hi go to the CTA's private slice of the segment's tier-1
+//                       list (when a slice is full — clustered candidates — to the segment's shared spill
+//                       list, one global atomic per spilled entry); candidates in [cut_lo, cut_hi) go to a
+//                       tier-2 slice that is only read when tier 1 turns out to hold fewer than top_k.
 //   B   segment_kernel  one CTA per segment: histogram of the listed candidates -> threshold bin (the lowest
 //                       bin still inside the top_k), counting sort on the score bins + exact in-bin rank
 //                       (score desc, anchor asc = tf.nn.top_k order), keep the first top_k, gather + decode
 //                       their boxes on demand, greedy NMS in batches against the kept list, write keep_top_k
 //                       rows zero padded.
-// The cut is a performance device only: a segment whose list ends up with fewer than top_k entries although
-// candidates were cut, whose slice overflowed, or whose threshold bin holds massive ties, is flagged and
-// redone by the exact general kernels (topk_segment_kernel + nms_kernel), which run only for flagged rows.
+// The cuts are a performance device only: a segment whose two tiers together hold fewer than top_k entries
+// although candidates below cut_lo were dropped (a 4x estimation error), whose spill list overflowed, or whose
+// threshold bin holds massive ties, is flagged and redone by the exact general kernels (topk_segment_kernel +
+// nms_kernel), which run only for flagged rows.
 // Prediction depths other than 11 use the plain-load two-pass kernels (hist_kernel, thresh_kernel,
 // collect_kernel: full histogram, exact threshold bin) in front of the same segment kernel.
 #include "select_topk.cuh"
@@ -117,7 +124,7 @@ hist_kernel(const __grid_constant__ StreamParams P, unsigned* __restrict__ g_his
 // TMA-staged scan (prediction depth C known at compile time)
 // ------------------------------------------------------------------------------------------
 constexpr int kScanBlock = 256;     // threads = anchors per tile
-constexpr int kScanStages = 2;      // TMA tiles in flight per CTA (ring of shared-memory buffers; 4 measured slower: fewer CTAs per SM)
+constexpr int kScanStages = 2;      // TMA tiles in flight per CTA (ring of shared-memory buffers; 3 / 4 measured slower: fewer CTAs per SM)
 constexpr int kListCap = 4096;      // per segment candidate list entries (8 B each)
 constexpr int kMaxChunks = 64;      // CTAs per image; each owns kListCap / chunks list slots per class
 
@@ -146,7 +153,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 constexpr int kSampleBins = 256;    // coarse bins (4 score bins each) of the sampled histogram
-constexpr int kSampleStride = 8;    // every 8th 256-anchor tile is sampled
+constexpr int kSampleStride = 19;   // every 19th anchor is sampled (coprime with the anchor shapes per cell)
+constexpr int kSamplePhase = 9;     // anchors 9, 28, 47, ...
+constexpr int kSpillCap = 2048;     // per segment: entries that did not fit their CTA's slice
 
 struct ScanParams {
   LayeredF probs;
@@ -155,17 +164,26 @@ struct ScanParams {
   int chunks, spc;                     // CTAs per image, list slots per (class, CTA)
   float thr;
   unsigned* g_shist;                   // [rows][kSampleBins] histogram of the sampled tiles (sample_kernel)
-  int sample_target;                   // sampled candidates that must lie at or above the estimated cut
-  int* g_est;                          // [rows] estimated cut as a score bin (0: no cut beyond thr)
-  unsigned* g_cnt1;                    // [rows][kMaxChunks] candidates written by each CTA
+  int target_hi, target_lo;            // sampled candidates that must lie at or above cut_hi / cut_lo
+  int* g_est;                          // [rows] cut_lo as a score bin (0: nothing below it was dropped)
+  unsigned* g_cnt1;                    // [rows][kMaxChunks] tier-1 candidates written by each CTA
+  unsigned* g_cnt2;                    // [rows][kMaxChunks] tier-2 candidates written by each CTA
+  unsigned long long* g_list2;         // [rows][kListCap]  per-CTA tier-2 slices
+  unsigned* g_lo_over;                 // [rows] set when a tier-2 slice overflowed (tier 2 incomplete)
+  unsigned* g_any;                     // [1] set when any segment is flagged for the exact general kernels
+  int b0, nb;                          // images [b0, b0 + nb) of the batch are scanned by this launch
   unsigned* g_over;                    // [rows] set when a CTA ran out of list slots: exact general kernels redo the segment
   unsigned long long* g_list;          // [rows][kListCap]  per-CTA slices
+  unsigned* g_spill_cnt;               // [rows] entries appended to the spill list (may exceed kSpillCap: overflow)
+  unsigned long long* g_spill;         // [rows][kSpillCap] entries whose slice was full
 };
 
 template <int C>
 struct ScanShared {
-  unsigned cnt[C];
-  float cut[C];                        // per-class append threshold: max(thr, estimated cut)
+  unsigned cnt[C], cnt2[C];            // tier-1 / tier-2 entries of this CTA
+  float cut_hi[C], cut_lo[C];          // per-class tier thresholds: max(thr, estimated cut)
+  unsigned spill_full[C];              // set once the segment's spill list is exhausted
+  unsigned lo_over[C];                 // set when this CTA's tier-2 slice overflowed
 };
 
 // probabilities of one anchor in registers: e[] holds the C scores, or (LOGITS, f-1) the logits, which are
@@ -187,21 +205,38 @@ __device__ __forceinline__ void row_probs(float (&e)[C], float& mx, float& rinv)
   }
 }
 
-// Pre-pass: histogram (coarse bins) of the candidates of every kSampleStride-th tile.  From it the scan
-// pass estimates, per segment, a score cut above which about 2 * top_k candidates lie, and only appends
-// those.  The estimate cannot affect the result: a segment whose list then holds fewer than top_k entries
-// (or overflows) is redone by the exact general kernels.
+// Pre-pass: histogram (coarse bins) of the candidates of every kSampleStride-th anchor.  From it the scan
+// pass estimates, per segment, the two score cuts.  The estimates cannot affect the result: a segment whose
+// lists then hold fewer than top_k entries although candidates were dropped (or overflow) is redone by the
+// exact general kernels.
 template <int C, bool LOGITS>
 __global__ void __launch_bounds__(256)
 sample_kernel(const __grid_constant__ ScanParams P) {
-  const int b = blockIdx.y;
-  const int n = (blockIdx.x * kSampleStride + kSampleStride / 2) * 256 + threadIdx.x;
-  if (n >= P.L.n_total) return;
-  const int l = layer_of(P.L, n);
-  const float* row = P.probs.base[l] + (long long)b * P.probs.stride[l] + (long long)(n - P.L.offset[l]) * C;
+  __shared__ float s_rows[8][32 * C];                  // per warp: its 32 sampled rows
+  pdl_launch_dependents();                             // the scan pass may start its prologue now
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = ((blockIdx.x * 8 + warp) * 32 + lane) * kSampleStride + kSamplePhase;
+  const bool valid = n < P.L.n_total;
+  const float* row = nullptr;
+  if (valid) {
+    const int l = layer_of(P.L, n);
+    row = P.probs.base[l] + (long long)b * P.probs.stride[l] + (long long)(n - P.L.offset[l]) * C;
+  }
+  // The rows of a warp lie kSampleStride * C floats apart: a lane-per-row load would touch 32 cache lines per
+  // instruction.  Stage them with lane-per-ELEMENT loads instead (element idx of the warp's 32 * C floats belongs
+  // to row idx / C): ~3 lines per instruction, then every lane reads its own row from shared memory.
+  float* mine = s_rows[warp];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int idx = j * 32 + lane, r = idx / C, k = idx - r * C;
+    const unsigned long long pr = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, r);
+    if (pr) mine[idx] = __ldg(reinterpret_cast<const float*>((uintptr_t)pr) + k);
+  }
+  __syncwarp();
+  if (!valid) return;
   float e[C], mx = 0.f, rinv = 0.f;
 #pragma unroll
-  for (int c = 0; c < C; ++c) e[c] = __ldg(row + c);
+  for (int c = 0; c < C; ++c) e[c] = mine[lane * C + c];          // stride C words: conflict-free for odd C
   row_probs<C, LOGITS>(e, mx, rinv);
   unsigned cand = 0;
 #pragma unroll
@@ -211,7 +246,7 @@ sample_kernel(const __grid_constant__ ScanParams P) {
   while (cand) {
     const int c = __ffs(cand) - 1;
     cand &= cand - 1;
-    float s = __ldg(row + c);
+    float s = mine[lane * C + c];
     if constexpr (LOGITS) s = __fmul_rn(softmax_exp(s, mx), rinv);
     atomicAdd(h + (size_t)c * P.batch * kSampleBins + (score_bin(s) >> 2), 1u);
   }
@@ -224,8 +259,8 @@ sample_kernel(const __grid_constant__ ScanParams P) {
 // candidate's probability is recomputed with the same instructions when its key is built.
 template <int C, bool LOGITS>
 __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<C>& S, const float (&cut)[C], bool valid,
-                                            const float* __restrict__ row, int n, int b) {
-  unsigned long long* const slice0 = P.g_list + (size_t)b * kListCap + (size_t)blockIdx.x * P.spc;
+                                            const float* __restrict__ row, int n, int b, int chunk_id) {
+  const size_t slice_off = (size_t)b * kListCap + (size_t)chunk_id * P.spc;
   const size_t slice_stride = (size_t)P.batch * kListCap;
   unsigned cand = 0;
   float mx = 0.f, rinv = 0.f;
@@ -244,15 +279,37 @@ __device__ __forceinline__ void scan_anchor(const ScanParams& P, ScanShared<C>& 
     cand &= cand - 1;
     float s = row[c];
     if constexpr (LOGITS) s = __fmul_rn(softmax_exp(s, mx), rinv);
-    if (S.cnt[c] < (unsigned)P.spc) {                     // (dense inputs: no atomic once the slice is full)
+    const unsigned long long entry = ((unsigned long long)__float_as_uint(s) << 32) | nkey;
+    if (s < S.cut_hi[c]) {                                // tier 2: only read when tier 1 holds fewer than top_k
+      bool placed2 = false;
+      if (S.cnt2[c] < (unsigned)P.spc) {
+        const unsigned pos = atomicAdd(&S.cnt2[c], 1u);
+        if (pos < (unsigned)P.spc) {
+          P.g_list2[slice_off + (size_t)c * slice_stride + pos] = entry;
+          placed2 = true;
+        }
+      }
+      if (!placed2) S.lo_over[c] = 1u;
+      continue;
+    }
+    bool placed = false;
+    if (S.cnt[c] < (unsigned)P.spc) {                     // (no shared atomic once the slice is full)
       const unsigned pos = atomicAdd(&S.cnt[c], 1u);
-      if (pos < (unsigned)P.spc)
-        slice0[(size_t)c * slice_stride + pos] = ((unsigned long long)__float_as_uint(s) << 32) | nkey;
+      if (pos < (unsigned)P.spc) {
+        P.g_list[slice_off + (size_t)c * slice_stride + pos] = entry;
+        placed = true;
+      }
+    }
+    if (!placed && !S.spill_full[c]) {                    // slice full: the segment's shared spill list
+      const size_t r = (size_t)c * P.batch + b;
+      const unsigned q = atomicAdd(&P.g_spill_cnt[r], 1u);
+      if (q < (unsigned)kSpillCap) P.g_spill[r * kSpillCap + q] = entry;
+      else S.spill_full[c] = 1u;                          // (dense inputs: no global atomic once the spill list is full)
     }
   }
 }
 
-template <int C, bool LOGITS>
+template <int C, bool LOGITS, int kScanStages>
 __global__ void __launch_bounds__(kScanBlock)
 scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -261,9 +318,16 @@ scan_kernel(const __grid_constant__ ScanParams P) {
   __shared__ __align__(8) unsigned long long s_bar[kScanStages];
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.y;
-  if (tid < C) S.cnt[tid] = 0u;
-  // per-class cut from the sampled histogram: the highest coarse bin t with count(bins >= t) >= target
+  pdl_launch_dependents();                             // the next kernel of the stream may be scheduled (it waits for this grid)
+  if (tid == 0) {
+    for (int q = 0; q < kScanStages; ++q) mbar_init(&s_bar[q], 1);
+    fence_mbar_init();
+  }
+  pdl_wait();                                          // sampled histogram complete
+  unsigned phases = 0;                                 // bit q = parity of barrier q
+  const int b = P.b0 + blockIdx.y, chunk_id = blockIdx.x;   // grid = (chunks per image, images)
+  if (tid < C) { S.cnt[tid] = 0u; S.cnt2[tid] = 0u; S.spill_full[tid] = 0u; S.lo_over[tid] = 0u; }
+  // per-class cuts from the sampled histogram: the highest coarse bin t with count(bins >= t) >= target
   for (int c = tid >> 5; c < C; c += kScanBlock / 32) {
     const int lane = tid & 31;
     const unsigned* h = P.g_shist + ((size_t)c * P.batch + b) * kSampleBins + lane * 8;
@@ -276,35 +340,39 @@ scan_kernel(const __grid_constant__ ScanParams P) {
       const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
       if (lane + o < 32) suf += x;
     }
-    const unsigned above = suf - sum, target = (unsigned)P.sample_target;
-    int t = 0;
-    if (above < target && suf >= target) {             // exactly one lane when the row holds >= target samples
-      unsigned acc = above;
+    const unsigned above = suf - sum;
+    int tb[2];
 #pragma unroll
-      for (int q = 7; q >= 0; --q) {
-        acc += v[q];
-        if (acc >= target) { t = lane * 8 + q; break; }
+    for (int which = 0; which < 2; ++which) {
+      const unsigned target = (unsigned)(which == 0 ? P.target_hi : P.target_lo);
+      int t = 0;
+      if (above < target && suf >= target) {           // exactly one lane when the row holds >= target samples
+        unsigned acc = above;
+#pragma unroll
+        for (int q = 7; q >= 0; --q) {
+          acc += v[q];
+          if (acc >= target) { t = lane * 8 + q; break; }
+        }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
-    if (lane == 0) {
-      const float cut = fmaxf(P.thr, (float)(4 * t) * (1.f / (float)kBins));     // score_bin(s) >= 4t  <=>  s >= 4t / 1024
-      S.cut[c] = cut;
-      if (blockIdx.x == 0) P.g_est[(size_t)c * P.batch + b] = cut > P.thr ? 4 * t : 0;
+      for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+      tb[which] = t;
     }
-  }
-  if (tid == 0) {
-    for (int q = 0; q < kScanStages; ++q) mbar_init(&s_bar[q], 1);
-    fence_mbar_init();
+    if (lane == 0) {
+      // score_bin(s) >= 4t  <=>  s >= 4t / 1024
+      const float hi = fmaxf(P.thr, (float)(4 * tb[0]) * (1.f / (float)kBins));
+      const float lo = fmaxf(P.thr, (float)(4 * tb[1]) * (1.f / (float)kBins));
+      S.cut_hi[c] = hi;
+      S.cut_lo[c] = fminf(lo, hi);
+      if (chunk_id == 0) P.g_est[(size_t)c * P.batch + b] = lo > P.thr ? 4 * tb[1] : 0;
+    }
   }
   __syncthreads();
   float cut[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) cut[c] = S.cut[c];
+  for (int c = 0; c < C; ++c) cut[c] = S.cut_lo[c];
 
-  const int A0 = blockIdx.x * P.chunk, A1 = min(A0 + P.chunk, P.L.n_total);
-  unsigned phases = 0;                                 // bit q = parity of barrier q
+  const int A0 = chunk_id * P.chunk, A1 = min(A0 + P.chunk, P.L.n_total);
   for (int l = 0; l < P.L.n_layers; ++l) {
     const int lo = max(A0, P.L.offset[l]), hi = min(A1, P.L.offset[l + 1]);
     if (lo >= hi) continue;
@@ -331,7 +399,7 @@ scan_kernel(const __grid_constant__ ScanParams P) {
     const int nscalar = (t0 - lo) + (hi - t1);
     for (int i = tid; i < nscalar; i += kScanBlock) {
       const int n = i < t0 - lo ? lo + i : t1 + (i - (t0 - lo));
-      scan_anchor<C, LOGITS>(P, S, cut, true, slab + (long long)n * C, n, b);
+      scan_anchor<C, LOGITS>(P, S, cut, true, slab + (long long)n * C, n, b, chunk_id);
     }
     for (int t = 0; t < ntiles; ++t) {
       const int q = t % kScanStages;
@@ -342,16 +410,18 @@ scan_kernel(const __grid_constant__ ScanParams P) {
       mbar_wait(&s_bar[q], (phases >> q) & 1u);
       phases ^= 1u << q;
       // row stride C words: conflict-free across lanes for odd C
-      scan_anchor<C, LOGITS>(P, S, cut, tid < cnt, s_tiles + q * kScanBlock * C + tid * C, a0 + tid, b);
+      scan_anchor<C, LOGITS>(P, S, cut, tid < cnt, s_tiles + q * kScanBlock * C + tid * C, a0 + tid, b, chunk_id);
       __syncthreads();                                   // tile consumed: its buffer may be refilled
     }
   }
   __syncthreads();
   if (tid < C) {
     const size_t r = (size_t)tid * P.batch + b;
-    const unsigned c = S.cnt[tid];
-    P.g_cnt1[r * kMaxChunks + blockIdx.x] = c < (unsigned)P.spc ? c : (unsigned)P.spc;
-    if (c >= (unsigned)P.spc) P.g_over[r] = 1u;          // out of slots (conservatively also when exactly full)
+    const unsigned c = S.cnt[tid], c2 = S.cnt2[tid];
+    P.g_cnt1[r * kMaxChunks + chunk_id] = c < (unsigned)P.spc ? c : (unsigned)P.spc;
+    P.g_cnt2[r * kMaxChunks + chunk_id] = c2 < (unsigned)P.spc ? c2 : (unsigned)P.spc;
+    if (S.lo_over[tid]) P.g_lo_over[r] = 1u;
+    if (S.spill_full[tid]) { P.g_over[r] = 1u; *P.g_any = 1u; }   // the spill list overflowed: exact general kernels redo the segment
   }
 }
 
@@ -430,10 +500,17 @@ struct SegParams {
   // (force_dense: prediction depths without the TMA scan) one list per segment ([rows][cap], cnt2)
   const unsigned long long* list1;
   const unsigned* cnt1;
+  const unsigned long long* list2;   // tier-2 slices ([rows][kListCap], counts cnt1b [rows][kMaxChunks]): candidates in [cut_lo, cut_hi)
+  const unsigned* cnt1b;
+  const unsigned* lo_over;           // [rows] tier 2 is incomplete (a slice overflowed)
+  const unsigned* spill_cnt;         // [rows] spill entries (values above kSpillCap: overflow, flagged by the scan pass)
+  const unsigned long long* spill;   // [rows][kSpillCap]
   const unsigned* cnt2;
   const int* est;            // [rows] score bin below which the scan pass dropped candidates (0: none dropped)
   long long* dbg;            // optional per-segment phase timestamps (rod_debug_set_timing), else NULL
   unsigned* over;            // out: 1 when the segment must be redone by the exact general kernels
+  unsigned* any;             // out: 1 when any segment is
+  int b0, nb;                // images [b0, b0 + nb) of the batch: one CTA per (class, image of the range)
   int chunks, spc, force_dense;
 };
 
@@ -479,24 +556,33 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   __shared__ unsigned long long s_deadw[kSegWarps], s_sel;      // per-warp "suppressed by the kept list" masks of a batch
   __shared__ int s_nsel;
 
-  const long long r = blockIdx.x;
-  const int c = (int)(r / P.batch), b = (int)(r % P.batch);
-  if (c == P.ignore_class) return;
+  const int c = (int)(blockIdx.x / P.nb), b = P.b0 + (int)(blockIdx.x % P.nb);
+  const long long r = (long long)c * P.batch + b;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();                             // the fallback kernels may be scheduled (they wait for this grid)
+  if (out_counts && tid == 0) out_counts[r] = 0;       // (flagged rows: the general kernels add theirs)
+  if (c == P.ignore_class) return;
+  pdl_wait();                                          // candidate lists of the preceding grid complete
 #define SEG_T(i) do { if (P.dbg != nullptr && tid == 0) P.dbg[r * 8 + (i)] = clock64(); } while (0)
   SEG_T(0);
   // ---- 0. histogram of the segment's listed candidates -> threshold bin (the lowest bin still inside
   // the top_k) and the start offset of every bin in descending order.
   __shared__ int s_n, s_tbv;
-  __shared__ unsigned s_part[kMaxChunks];
+  __shared__ unsigned s_part[kMaxChunks], s_part2[kMaxChunks];
   __shared__ unsigned s_wsum[kSegWarps];
+  __shared__ int s_tot, s_has2;
   const bool dense = P.force_dense != 0;
   const unsigned long long* base;
+  const unsigned long long* base2 = nullptr;
+  const unsigned long long* spill = nullptr;
+  unsigned n_spill = 0;
   int parts, pstride;
+  if (tid == 0) s_has2 = 0;
+  __syncthreads();
   if (dense) {
     const unsigned n_in = P.cnt2[r];
     if (n_in > (unsigned)cap) {                       // massive ties in the threshold bin: exact kernels redo it
-      if (tid == 0) P.over[r] = 1u;
+      if (tid == 0) { P.over[r] = 1u; *P.any = 1u; }
       return;
     }
     base = g_list + r * cap; parts = 1; pstride = 0;
@@ -504,19 +590,29 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   } else {
     if (P.over[r] != 0u) return;                      // a scan CTA ran out of list slots: exact kernels redo it
     base = P.list1 + r * kListCap; parts = P.chunks; pstride = P.spc;
-    if (tid < parts) s_part[tid] = P.cnt1[r * kMaxChunks + tid];
+    base2 = P.list2 + r * kListCap;
+    if (tid < parts) {
+      s_part[tid] = P.cnt1[r * kMaxChunks + tid];
+      const unsigned n2 = P.cnt1b[r * kMaxChunks + tid];
+      s_part2[tid] = n2;
+      if (n2) s_has2 = 1;
+    }
+    n_spill = min(P.spill_cnt[r], (unsigned)kSpillCap);
+    spill = P.spill + r * kSpillCap;
   }
   unsigned long long* s_tmp = s_keys + cap;
   unsigned* s_h = reinterpret_cast<unsigned*>(s_keys + 2 * cap);          // [kBins]
-  for (int i = tid; i < kBins; i += kSegBlock) s_h[i] = 0u;
-  __syncthreads();
+  bool use2 = false;                                   // tier 2 joins when tier 1 holds fewer than top_k
   // Visits every listed entry: a warp takes whole slices (a slice holds ~100 entries once the scan pass cuts
   // at ~2 * top_k per segment), four independent loads per lane; a single long list is split over the block.
   auto for_each_entry = [&](auto&& fn) {
     const int stride = parts == 1 ? kSegBlock : 32, first = parts == 1 ? tid : lane;
-    for (int part = parts == 1 ? 0 : warp; part < parts; part += kSegWarps) {
-      const unsigned n = s_part[part];
-      const unsigned long long* sl = base + (size_t)part * pstride;
+    const int nparts = use2 ? 2 * parts : parts;       // parts .. 2 * parts - 1: the tier-2 slices
+    for (int pp = parts == 1 ? 0 : warp; pp < nparts; pp += kSegWarps) {
+      const bool second = pp >= parts;
+      const int part = second ? pp - parts : pp;
+      const unsigned n = second ? s_part2[part] : s_part[part];
+      const unsigned long long* sl = (second ? base2 : base) + (size_t)part * pstride;
       for (unsigned j0 = 0; j0 < n; j0 += 4 * stride) {
         unsigned long long ev[4];
 #pragma unroll
@@ -529,7 +625,21 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
           if ((unsigned)(ev[u] >> 32) != 0u) fn(ev[u]);   // empty slots are 0; real entries have score >= thr > 0
       }
     }
+    for (unsigned j0 = 0; j0 < n_spill; j0 += 4 * kSegBlock) {       // spill list (usually empty): the whole block
+      unsigned long long ev[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned j = j0 + u * kSegBlock + tid;
+        ev[u] = j < n_spill ? spill[j] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if ((unsigned)(ev[u] >> 32) != 0u) fn(ev[u]);
+    }
   };
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int i = tid; i < kBins; i += kSegBlock) s_h[i] = 0u;
+  __syncthreads();
   for_each_entry([&](unsigned long long e) { atomicAdd(&s_h[score_bin(__uint_as_float((unsigned)(e >> 32)))], 1u); });
   __syncthreads();
   {
@@ -557,17 +667,23 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
       s_tbv = 0;
       s_n = (int)c0;
     }
+    if (tid == 0) s_tot = (int)c0;
     s_h[4 * tid + 3] = above;                          // start offset of every bin in the sorted order
     s_h[4 * tid + 2] = c3;
     s_h[4 * tid + 1] = c2;
     s_h[4 * tid] = c1;
   }
   __syncthreads();
+  // tier 1 holds fewer than top_k candidates (cut_hi was estimated too high): take tier 2 in as well
+  if (dense || use2 || s_tot >= k || !s_has2) break;
+  use2 = true;
+  __syncthreads();
+  }
   const int cnt = s_n, tb = s_tbv;
-  // fewer than k listed although the scan pass dropped candidates below its estimated cut (the estimate
-  // was too high), or massive ties in the threshold bin: the exact general kernels redo the segment
-  if ((!dense && cnt < k && P.est[r] > 0) || cnt > cap) {
-    if (tid == 0) P.over[r] = 1u;
+  // fewer than k listed although the scan pass dropped candidates below cut_lo (or lost tier-2 entries), or
+  // massive ties in the threshold bin: the exact general kernels redo the segment
+  if ((!dense && cnt < k && (P.est[r] > 0 || P.lo_over[r] != 0u)) || cnt > cap) {
+    if (tid == 0) { P.over[r] = 1u; *P.any = 1u; }
     return;
   }
   SEG_T(1);
@@ -815,7 +931,13 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   }
   if (out_counts) {
     nonzero = __reduce_add_sync(0xffffffffu, nonzero);
-    if (lane == 0 && nonzero) atomicAdd(out_counts + r, nonzero);
+    if (lane == 0) s_wsum[warp] = (unsigned)nonzero;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned total = 0;
+      for (int w = 0; w < kSegWarps; ++w) total += s_wsum[w];
+      out_counts[r] = (int)total;
+    }
   }
   SEG_T(5);
   if (P.dbg != nullptr && tid == 0) { P.dbg[r * 8 + 6] = nk; P.dbg[r * 8 + 7] = cnt; }
@@ -823,7 +945,6 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
 }
 
 static long long* g_seg_dbg = nullptr;
-
 static size_t seg_smem_bytes(int cap, int k, int keep) {
   return seg_region_a(cap, k, keep) + (size_t)k * (16 + 16 + 4 + 4) + (size_t)keep * 4 + 16;
 }
@@ -837,8 +958,9 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t stream_workspace_bytes(int batch, int n_classes, int top_k) {
   const size_t rows = (size_t)batch * n_classes;
-  return align256(rows * (4 + 4 + kSampleBins * 4 + kBins * 4)) + align256(rows * 4) + align256(rows * kMaxChunks * 4) +
-         align256(rows * (size_t)kListCap * 8) + align256(rows * (size_t)stream_cap(top_k) * 8) + 256;
+  return align256(rows * (4 + 4 + 4 + 4 + kSampleBins * 4 + kBins * 4) + 16) + align256(rows * 4) + 2 * align256(rows * kMaxChunks * 4) +
+         2 * align256(rows * (size_t)kListCap * 8) + align256(rows * (size_t)kSpillCap * 8) +
+         align256(rows * (size_t)stream_cap(top_k) * 8) + 256;
 }
 
 // Enqueues S, A, B.  *over_out (device, [rows]) is non-zero for segments the exact general
@@ -847,29 +969,52 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
                          const LayeredF* refine, const LayeredF* det, int batch, int C, int logits, int ignore_class,
                          float select_thr, float nms_thr, int top_k, int keep, const float* clip, float* out_scores,
                          float* out_boxes, int32_t* out_counts, void* ws, const unsigned** over_out, int* cap_out,
-                         cudaStream_t st) {
+                         const unsigned** any_out, cudaStream_t st) {
   ROD_REQUIRE(!logits || C == 11, "launch_detect_stream: fused softmax needs 11 classes (got %d)", C);
   const size_t rows = (size_t)batch * C;
   const int cap = stream_cap(top_k);
   unsigned char* p = reinterpret_cast<unsigned char*>(ws);
-  // zero-initialised head of the workspace: over flags, dense counters, sampled histogram (TMA path) and the
-  // full histogram (plain-load path only)
+  // zero-initialised head of the workspace: over flags, dense counters, spill counters, sampled histogram (TMA
+  // path) and the full histogram (plain-load path only)
   unsigned* g_over = reinterpret_cast<unsigned*>(p);
   unsigned* g_cnt2 = g_over + rows;
-  unsigned* g_shist = g_cnt2 + rows;
+  unsigned* g_spill_cnt = g_cnt2 + rows;
+  unsigned* g_lo_over = g_spill_cnt + rows;
+  unsigned* g_any = g_lo_over + rows;                    // [4] (one flag, padded)
+  unsigned* g_shist = g_any + 4;
   unsigned* g_hist = g_shist + rows * kSampleBins;
-  const size_t zero_tma = rows * (4 + 4 + kSampleBins * 4), zero_all = zero_tma + rows * kBins * 4;
+  const size_t zero_tma = rows * (4 + 4 + 4 + 4 + kSampleBins * 4) + 16, zero_all = zero_tma + rows * kBins * 4;
   p += align256(zero_all);
   int* g_tbin = reinterpret_cast<int*>(p);                     // plain-load path: threshold bins; TMA path: estimated cuts
   p += align256(rows * 4);
   unsigned* g_cnt1 = reinterpret_cast<unsigned*>(p);           // [rows][kMaxChunks], fully written by the scan pass
   p += align256(rows * kMaxChunks * 4);
+  unsigned* g_cnt1b = reinterpret_cast<unsigned*>(p);          // the same for tier 2
+  p += align256(rows * kMaxChunks * 4);
   unsigned long long* g_list = reinterpret_cast<unsigned long long*>(p);
   p += align256(rows * (size_t)kListCap * 8);
+  unsigned long long* g_list_lo = reinterpret_cast<unsigned long long*>(p);
+  p += align256(rows * (size_t)kListCap * 8);
+  unsigned long long* g_spill = reinterpret_cast<unsigned long long*>(p);
+  p += align256(rows * (size_t)kSpillCap * 8);
   unsigned long long* g_list2 = reinterpret_cast<unsigned long long*>(p);   // [rows][cap]
-  int n_chunks = 1, spc = 512, force_dense = 0;
+  int n_chunks = 1, spc = 512;
   ROD_CUDA(cudaMemsetAsync(g_over, 0, C == 11 ? zero_tma : zero_all, st));
-  if (out_counts) ROD_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * rows, st));
+  const size_t seg_smem = seg_smem_bytes(cap, top_k, keep);
+  ROD_REQUIRE(seg_smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep, seg_smem);
+  ROD_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
+  auto fill_seg_params = [&](SegParams& G) {
+    G.has_loc = loc ? 1 : 0;
+    G.loc = loc ? *loc : *refine;
+    G.refine = loc ? *loc : *refine;
+    G.det = loc ? *loc : *det;
+    G.center = anchors_center;
+    G.L = L; G.batch = batch; G.ignore_class = ignore_class; G.cap = cap; G.k = top_k; G.keep = keep;
+    G.nms_thr = nms_thr; G.clip = clip;
+    G.cnt2 = g_cnt2; G.over = g_over; G.any = g_any; G.dbg = g_seg_dbg;
+    G.list1 = g_list; G.cnt1 = g_cnt1; G.est = g_tbin; G.spill_cnt = g_spill_cnt; G.spill = g_spill;
+    G.list2 = g_list_lo; G.cnt1b = g_cnt1b; G.lo_over = g_lo_over;
+  };
 
   if (C == 11) {
     // ---- sampled pre-pass + TMA-staged single pass
@@ -877,18 +1022,18 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     SP.probs = probs; SP.L = L; SP.batch = batch; SP.thr = select_thr;
     SP.ignore_class = (ignore_class >= 0 && ignore_class < 11) ? ignore_class : 31;   // 31: no class bit ever matches
     SP.g_shist = g_shist; SP.g_est = g_tbin; SP.g_cnt1 = g_cnt1; SP.g_over = g_over; SP.g_list = g_list;
-    // sampled tiles: kSampleStride/2, kSampleStride/2 + kSampleStride, ... ; the cut keeps about 2 * top_k
-    // candidates per segment (5 sigma above top_k for a binomial sample of 1/8)
-    const int ntiles = (L.n_total + 255) / 256;
-    const int stiles = (ntiles + kSampleStride / 2) / kSampleStride;
-    long long sampled = 0;
-    for (int t = 0; t < stiles; ++t) {
-      const long long a0 = (long long)(t * kSampleStride + kSampleStride / 2) * 256;
-      if (a0 < L.n_total) sampled += (L.n_total - a0 < 256 ? L.n_total - a0 : 256);
-    }
+    SP.g_spill_cnt = g_spill_cnt; SP.g_spill = g_spill;
+    SP.g_cnt2 = g_cnt1b; SP.g_list2 = g_list_lo; SP.g_lo_over = g_lo_over; SP.g_any = g_any;
+    // sampled anchors: kSamplePhase, kSamplePhase + kSampleStride, ...  Tier 1 keeps about 1.6 * top_k candidates per
+    // segment (a too-high cut_hi only costs reading tier 2 as well), tiers 1 + 2 together about 4 * top_k: falling
+    // below top_k there takes a 4x estimation error (> 8 sigma of the binomial sample at top_k = 400)
+    const int sampled = L.n_total > kSamplePhase ? (L.n_total - kSamplePhase + kSampleStride - 1) / kSampleStride : 0;
+    const int stiles = (sampled + 255) / 256;
     const double frac = L.n_total > 0 ? (double)sampled / (double)L.n_total : 0.0;
-    SP.sample_target = (int)(2.0 * top_k * frac + 0.5);
-    if (SP.sample_target < 32 || stiles < 2) SP.sample_target = 0x7fffffff;      // too few samples: never cut
+    SP.target_hi = (int)(1.6 * top_k * frac + 0.5);
+    SP.target_lo = (int)(4.0 * top_k * frac + 0.5);
+    const bool use_cut = SP.target_hi >= 24 && sampled >= 512;                    // too few samples: never cut
+    if (!use_cut) SP.target_hi = SP.target_lo = 0x7fffffff;
     int chunks = (4 * sm_count() + batch - 1) / batch;          // one wave of ~4 CTAs per SM (8 per SM measured slower)
     chunks = chunks < 8 ? 8 : (chunks > 32 ? 32 : chunks);     // >= 8: list slices of at most 512 entries
     int chunk = (L.n_total + chunks - 1) / chunks;
@@ -898,20 +1043,30 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     SP.chunk = chunk;
     SP.chunks = n_chunks = chunks;
     SP.spc = spc = kListCap / chunks < 512 ? kListCap / chunks : 512;
-    if (SP.sample_target != 0x7fffffff) {
+    SP.b0 = 0; SP.nb = batch;
+    if (use_cut) {
       auto ks = logits ? sample_kernel<11, true> : sample_kernel<11, false>;
       ks<<<dim3(stiles, batch), 256, 0, st>>>(SP);
       ROD_LAUNCH_CHECK("sample_kernel");
     }
-    const dim3 grid(chunks, batch);
-    const size_t smem0 = kScanStages * sizeof(float) * kScanBlock * 11 + sizeof(ScanShared<11>);
-    auto k0 = logits ? scan_kernel<11, true> : scan_kernel<11, false>;
+    // One stream, programmatic launches: each kernel is scheduled while its predecessor drains and waits
+    // (pdl_wait) before it reads the predecessor's results.  (Measured and dropped: persistent scan CTAs walking
+    // the images in order with per-image completion counters so that segments start under the scan — the scan
+    // needs its ~4 CTAs per SM, 108 vs 77 us; and scanning the batch in 2 / 4 / 8 slices with the segment
+    // kernels forked to side streams through events — 103 / 120 / 165 us, the cross-stream edges cost more
+    // than the overlap returns.)
+    const size_t smem0 = (size_t)kScanStages * sizeof(float) * kScanBlock * 11 + sizeof(ScanShared<11>);
+    auto k0 = logits ? scan_kernel<11, true, kScanStages> : scan_kernel<11, false, kScanStages>;
     ROD_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-    k0<<<grid, kScanBlock, smem0, st>>>(SP);
-    ROD_LAUNCH_CHECK("scan_kernel");
+    ROD_CUDA(launch_pdl(k0, dim3(chunks, batch), dim3(kScanBlock), smem0, st, SP));
+    SegParams G;
+    fill_seg_params(G);
+    G.chunks = n_chunks; G.spc = spc; G.force_dense = 0;
+    G.b0 = 0; G.nb = batch;
+    ROD_CUDA(launch_pdl(segment_kernel, dim3((unsigned)rows), dim3(kSegBlock), seg_smem, st, G, (const unsigned long long*)g_list2,
+                        out_scores, out_boxes, out_counts));
   } else {
     // ---- generic prediction depth: plain-load two-pass kernels, every segment takes the dense route
-    force_dense = 1;
     StreamParams SP;
     SP.probs = probs; SP.L = L; SP.C = C; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;
     const int total_f = L.n_total * C;
@@ -931,25 +1086,15 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     ROD_LAUNCH_CHECK("thresh_kernel");
     collect_kernel<<<grid, kStreamBlock, 0, st>>>(SP, g_tbin, g_cnt2, g_list2, cap);
     ROD_LAUNCH_CHECK("collect_kernel");
+    SegParams G;
+    fill_seg_params(G);
+    G.chunks = 1; G.spc = 512; G.force_dense = 1;
+    G.b0 = 0; G.nb = batch;
+    segment_kernel<<<(unsigned)rows, kSegBlock, seg_smem, st>>>(G, g_list2, out_scores, out_boxes, out_counts);
+    ROD_LAUNCH_CHECK("segment_kernel");
   }
-
-  SegParams G;
-  G.has_loc = loc ? 1 : 0;
-  G.loc = loc ? *loc : *refine;
-  G.refine = loc ? *loc : *refine;
-  G.det = loc ? *loc : *det;
-  G.center = anchors_center;
-  G.L = L; G.batch = batch; G.ignore_class = ignore_class; G.cap = cap; G.k = top_k; G.keep = keep;
-  G.nms_thr = nms_thr; G.clip = clip;
-  G.cnt2 = g_cnt2; G.over = g_over; G.dbg = g_seg_dbg;
-  G.list1 = g_list; G.cnt1 = g_cnt1; G.est = g_tbin;
-  G.chunks = n_chunks; G.spc = spc; G.force_dense = force_dense;
-  const size_t smem = seg_smem_bytes(cap, top_k, keep);
-  ROD_REQUIRE(smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep, smem);
-  ROD_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  segment_kernel<<<(unsigned)rows, kSegBlock, smem, st>>>(G, g_list2, out_scores, out_boxes, out_counts);
-  ROD_LAUNCH_CHECK("segment_kernel");
   *over_out = g_over;
+  *any_out = g_any;
   *cap_out = 0;                                                 // fallback kernels run where over[r] > 0
   return ROD_OK;
 }
@@ -959,3 +1104,4 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
 // Debug hook (not part of the public header): per-segment clock64() stamps of the segment kernel's
 // phases, 8 x int64 per (class, image) row.  Pass NULL to switch it off.
 extern "C" void rod_debug_set_timing(long long* device_buf) { rod::g_seg_dbg = device_buf; }
+

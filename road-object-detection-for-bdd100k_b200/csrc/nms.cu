@@ -44,6 +44,7 @@ struct GatherBoxes {       // fused: candidates come sorted from the top-k kerne
   Layout L;
   int has_loc, batch;
   const unsigned* over_cnt;   // when set: only segments whose streaming list overflowed run here
+  const unsigned* over_any;   // when set: non-zero iff any segment is flagged
   unsigned over_cap;
 };
 
@@ -65,6 +66,10 @@ nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ Gath
   int* s_selected = s_src + n;                                                           // [keep]
   __shared__ int s_last, s_nsel;
 
+  if (FUSED) {
+    pdl_wait();                                        // launched while the top-k kernel still runs
+    if (gsrc.over_any != nullptr && *gsrc.over_any == 0u) return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // persistent over rows (the fused path launches a small grid that usually finds nothing to do)
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
@@ -222,7 +227,7 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
                          const LayeredF* refine, const LayeredF* det, int batch, int C, int logits, int ignore_class,
                          float select_thr, float nms_thr, int top_k, int keep, const float* clip, float* out_scores,
                          float* out_boxes, int32_t* out_counts, void* ws, const unsigned** cnt_out, int* cap_out,
-                         cudaStream_t st);
+                         const unsigned** any_out, cudaStream_t st);
 
 }  // namespace rod
 
@@ -306,6 +311,7 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   // ---- fast path (select_threshold > 0): streaming histogram select + per-segment sort/decode/NMS
   const LayeredF probs_l = to_layered_f(predictions, nl);
   const unsigned* over_cnt = nullptr;
+  const unsigned* over_any = nullptr;
   int over_cap = 0;
   // (fused softmax is specialised for 11 classes; other depths take the general path below)
   if (select_threshold > 0.f && (!logits || n_classes == 11)) {
@@ -316,7 +322,7 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
     if ((rc = launch_detect_stream(L, anchors_center, probs_l, localizations ? &loc_l : nullptr,
                                    localizations ? nullptr : &ref_l, localizations ? nullptr : &det_l, batch,
                                    n_classes, logits, ignore_class, select_threshold, nms_threshold, top_k, keep_top_k,
-                                   clip_box, out_scores, out_bboxes, out_counts, ws_stream, &over_cnt, &over_cap, st)))
+                                   clip_box, out_scores, out_bboxes, out_counts, ws_stream, &over_cnt, &over_cap, &over_any, st)))
       return rc;
   } else if (out_counts) {
     ROD_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * rows, st));
@@ -332,6 +338,7 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   src.logits = logits;
   src.thr = select_threshold;
   src.over_cnt = over_cnt;
+  src.over_any = over_any;
   src.over_cap = (unsigned)over_cap;
   if ((rc = launch_topk_selected(src, rows, top_k, ws_scores, ws_idx, st))) return rc;
 
@@ -346,6 +353,7 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   g.L = L;
   g.batch = batch;
   g.over_cnt = over_cnt;
+  g.over_any = over_any;
   g.over_cap = (unsigned)over_cap;
   const size_t smem = nms_smem_bytes(top_k, keep_top_k, false);
   ROD_REQUIRE(smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep_top_k, smem);
@@ -353,9 +361,8 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   ROD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DenseBoxes d{};
   const unsigned grid = over_cnt ? (unsigned)(rows < 4 * sm_count() ? rows : 4 * sm_count()) : (unsigned)rows;
-  k<<<grid, kNmsBlock, smem, st>>>(d, g, rows, top_k, nms_threshold, keep_top_k, ignore_class, clip_box,
-                                            out_scores, out_bboxes, nullptr, out_counts);
-  ROD_LAUNCH_CHECK("nms_kernel<fused>");
+  ROD_CUDA(launch_pdl(k, dim3(grid), dim3(kNmsBlock), smem, st, d, g, rows, top_k, nms_threshold, keep_top_k, ignore_class,
+                      clip_box, out_scores, out_bboxes, (int32_t*)nullptr, out_counts));
   return ROD_OK;
 }
 }  // namespace rod

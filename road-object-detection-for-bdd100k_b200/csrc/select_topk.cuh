@@ -9,6 +9,7 @@ struct DenseScores {
   const float* scores;
   int n;
   __device__ __forceinline__ int size() const { return n; }
+  __device__ __forceinline__ bool any_active() const { return true; }
   __device__ __forceinline__ bool row_active(long long) const { return true; }
   // returns the (masked) score; real == false marks entries whose box was zeroed by select
   __device__ __forceinline__ float fetch(long long r, int i, bool& real) const {
@@ -26,8 +27,10 @@ struct SelectedScores {
   int logits;                 // predictions are logits: softmax on the fly (same bits as the fused select)
   float thr;
   const unsigned* over_cnt;   // when set: only segments whose streaming list overflowed are active
+  const unsigned* over_any;   // when set: non-zero iff any segment is flagged (lets the whole grid leave at once)
   unsigned over_cap;
   __device__ __forceinline__ int size() const { return L.n_total; }
+  __device__ __forceinline__ bool any_active() const { return over_any == nullptr || *over_any != 0u; }
   __device__ __forceinline__ bool row_active(long long r) const {
     return (int)(r / batch) != ignore_class && (over_cnt == nullptr || over_cnt[r] > over_cap);
   }

@@ -8,13 +8,15 @@
 // GT walk overlaps ODM's loads / stores inside one launch.  Results are bit-identical to
 // rod_arm_match_encode followed by rod_odm_target (same device functions, same op order).
 //
-// Shape: grid = (CTAs per image, images); a CTA stages the image's GT boxes (corner form + area) in
-// shared memory ONCE and then walks `tpc` 128-anchor tiles spread over the whole anchor range (tile
-// x, x + X, x + 2X, ...: every CTA gets a mix of cheap small-anchor and expensive big-anchor tiles,
-// the expensive ones first), sized so that the grid is one resident wave.  Inside a tile a WARP owns
-// 32 consecutive anchors: it culls the GT list against the bounding box of its anchors with one
-// ballot per 32 GT boxes and walks the surviving bits in ascending GT index (= lowest-index
-// tie-break of tf.argmax), exactly like arm_jaccard_bigger_kernel.
+// Shape: one resident wave of persistent CTAs that pull work items (one 128-anchor tile of one image)
+// from a global counter, most expensive first (the tiles of the big-anchor layers meet every GT box, the
+// 64x64 layer's tiles only ~6 % of them; an image with 100 GT boxes costs ~10x one with 5): a static
+// partition leaves 40 % of the issue slots idle behind the slowest CTA.  A CTA stages the item's GT
+// boxes (corner form + area) in shared memory; inside the tile a WARP owns 32 consecutive anchors: it
+// culls the GT list against the bounding box of its anchors with one ballot per 32 GT boxes and walks
+// the surviving bits in ascending GT index (= lowest-index tie-break of tf.argmax), exactly like
+// arm_jaccard_bigger_kernel.  The counter pair lives in an 8-byte caller workspace that must be zero
+// before the first call and is left zero by every call (the last CTA to leave resets it).
 #include "common.cuh"
 
 namespace rod {
@@ -32,7 +34,8 @@ struct FusedParams {
   LayeredF refine_out;                  // ARM head output, per layer [B,...,4]
   float* out_gt; float* out_cb; int32_t* out_lab; int32_t* out_pos; int32_t* out_idx;     // ARM outputs (cb / lab / idx optional)
   float* det_gt; int32_t* det_mask; int32_t* det_lab; float* iou;                          // ODM outputs
-  int gmax, tiles, ctas_per_image;
+  int gmax, tiles, batch;
+  unsigned* sched;                      // [0] next work item, [1] CTAs that have left
 };
 
 template <typename LabelT>
@@ -41,26 +44,32 @@ target_fused_kernel(const __grid_constant__ FusedParams P) {
   extern __shared__ float4 s_box[];                         // [gmax] GT corners (net_tools.py:323)
   float* s_area = reinterpret_cast<float*>(s_box + P.gmax);  // [gmax] GT areas (:265)
 
+  __shared__ unsigned s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y;
   const int N = P.L.n_total;
   const float4 none = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);   // intersects nothing
+  const unsigned total = (unsigned)P.tiles * (unsigned)P.batch;
 
-  int count = P.counts ? P.counts[b] : P.gmax;
-  count = min(max(count, 0), P.gmax);
-  const float* gt_img = P.gtb + 4ll * b * P.gmax;
-  for (int g = tid; g < count; g += kTfBlock) {
-    const float4 gc = center_to_corner(ldg4(gt_img + 4ll * g));
-    const bool ok = (gc.z > gc.x) && (gc.w > gc.y);         // zero-extent GT: intersection 0 with everything
-    s_box[g] = ok ? gc : none;
-    s_area[g] = __fmul_rn(__fsub_rn(gc.z, gc.x), __fsub_rn(gc.w, gc.y));
-  }
+  if (tid == 0) s_item = atomicAdd(P.sched, 1u);
   __syncthreads();
-
-  // tiles x, x + X, ... of this CTA, highest (big anchors, most GT survivors) first
-  const int X = P.ctas_per_image;
-  int t = blockIdx.x + ((P.tiles - 1 - blockIdx.x) / X) * X;
-  for (; t >= 0; t -= X) {
+  unsigned item = s_item;
+  while (item < total) {
+    // item -> (tile, image): all images' last tile first, then the one before, ... (descending cost)
+    const int t = P.tiles - 1 - (int)(item / (unsigned)P.batch), b = (int)(item % (unsigned)P.batch);
+    __syncthreads();                                        // every warp has read s_item and is done with the GT list
+    if (tid == 0) s_item = atomicAdd(P.sched, 1u);          // next item: the fetch overlaps this tile
+    int count = P.counts ? P.counts[b] : P.gmax;
+    count = min(max(count, 0), P.gmax);
+    const float* gt_img = P.gtb + 4ll * b * P.gmax;
+    for (int g = tid; g < count; g += kTfBlock) {
+      const float4 gc = center_to_corner(ldg4(gt_img + 4ll * g));
+      const bool ok = (gc.z > gc.x) && (gc.w > gc.y);       // zero-extent GT: intersection 0 with everything
+      s_box[g] = ok ? gc : none;
+      s_area[g] = __fmul_rn(__fsub_rn(gc.z, gc.x), __fsub_rn(gc.w, gc.y));
+    }
+    __syncthreads();
+    item = s_item;
+    {
     const int n = t * kTfBlock + warp * 32 + lane;
     const bool valid = n < N;
     const int l = layer_of(P.L, valid ? n : N - 1);
@@ -98,7 +107,7 @@ target_fused_kernel(const __grid_constant__ FusedParams P) {
         }
       }
     }
-    if (!valid) continue;
+    if (valid) {
 
     // ---- ARM epilogue: threshold, gather the matched GT, encode (net_tools.py:405-416, 334-343)
     const bool pos = (best >= P.Ta.v[l]) && count > 0;
@@ -142,22 +151,31 @@ target_fused_kernel(const __grid_constant__ FusedParams P) {
     __stcs(P.det_mask + o, mk);
     __stcs(P.det_lab + o, lab * mk);                                 // :472
     __stcs(P.iou + o, j);
+    }   // valid
+    }   // tile
+  }
+  // leave: the last CTA resets the counters for the next launch
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(P.sched + 1, 1u) == gridDim.x - 1u) {
+      P.sched[0] = 0u;
+      P.sched[1] = 0u;
+    }
   }
 }
 
 static int g_tf_ctas_per_sm = 0;
-static int g_tf_tpc_override = 0;         // debug: tiles per CTA (0 = one resident wave)
 
 }  // namespace rod
 
-extern "C" void rod_debug_set_fused_tiles(int tiles_per_cta) { rod::g_tf_tpc_override = tiles_per_cta; }
+extern "C" size_t rod_target_fused_workspace_bytes(void) { return 8; }
 
 extern "C" int rod_target_fused(const rod_layout_t* layout, const float* anchors_corner, const float* anchors_center,
                                 const float* arm_thresholds, const float* odm_thresholds, const float* center_bboxes,
                                 const void* labels, int labels_i64, const int32_t* gt_counts, int batch, int gmax,
                                 const rod_layered_t* refine_out, float* gt, float* cbboxes, int32_t* out_labels,
                                 int32_t* pos_mask, int32_t* match_idx, float* det_gt, int32_t* det_mask,
-                                int32_t* det_labels, float* iou, void* stream) {
+                                int32_t* det_labels, float* iou, void* workspace, void* stream) {
   using namespace rod;
   int rc = check_layout(layout);
   if (rc) return rc;
@@ -166,6 +184,7 @@ extern "C" int rod_target_fused(const rod_layout_t* layout, const float* anchors
   ROD_REQUIRE(anchors_corner && anchors_center && arm_thresholds && odm_thresholds && center_bboxes && labels,
               "rod_target_fused: NULL input pointer");
   ROD_REQUIRE(gt && pos_mask && det_gt && det_mask && det_labels && iou, "rod_target_fused: NULL output pointer");
+  ROD_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "rod_target_fused: workspace is NULL or not 8-byte aligned");
   ROD_REQUIRE(batch >= 0 && gmax >= 1, "rod_target_fused: batch=%d gmax=%d invalid", batch, gmax);
   ROD_REQUIRE(batch <= 65535, "rod_target_fused: batch=%d exceeds 65535", batch);
   if (batch == 0) return ROD_OK;
@@ -190,13 +209,12 @@ extern "C" int rod_target_fused(const rod_layout_t* layout, const float* anchors
     ROD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, target_fused_kernel<long long>, kTfBlock, 2048));
     g_tf_ctas_per_sm = per > 0 ? per : 1;
   }
-  // one resident wave: tiles per CTA so that ctas_per_image * batch <= resident CTAs
-  const long long resident = (long long)g_tf_ctas_per_sm * sm_count();
-  int tpc = (int)(((long long)P.tiles * batch + resident - 1) / resident);
-  if (g_tf_tpc_override > 0) tpc = g_tf_tpc_override;
-  tpc = tpc < 1 ? 1 : tpc;
-  P.ctas_per_image = (P.tiles + tpc - 1) / tpc;
-  k<<<dim3(P.ctas_per_image, batch), kTfBlock, smem, (cudaStream_t)stream>>>(P);
+  // one resident wave of persistent CTAs (fewer when there is less work)
+  P.batch = batch;
+  P.sched = static_cast<unsigned*>(workspace);
+  const long long resident = (long long)g_tf_ctas_per_sm * sm_count(), items = (long long)P.tiles * batch;
+  const unsigned grid = (unsigned)(items < resident ? items : resident);
+  k<<<grid, kTfBlock, smem, (cudaStream_t)stream>>>(P);
   ROD_LAUNCH_CHECK("target_fused_kernel");
   return ROD_OK;
 }

@@ -24,6 +24,8 @@ topk_segment_kernel(const __grid_constant__ Src src, long long rows, int k, floa
   __shared__ int s_warp[kTopkBlock / 32];
   __shared__ unsigned s_bin, s_above, s_gt_count;
 
+  pdl_wait();                                          // (fused path: launched while the segment kernel still runs)
+  if (!src.any_active()) return;
   const int n = src.size();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // persistent over rows: the fused path launches a small grid that usually finds nothing to do
@@ -151,8 +153,8 @@ topk_segment_kernel(const __grid_constant__ Src src, long long rows, int k, floa
 int launch_topk_selected(const SelectedScores& src, long long rows, int k, float* out_scores, int32_t* out_idx,
                          cudaStream_t st) {
   const unsigned grid = src.over_cnt ? (unsigned)(rows < 2 * sm_count() ? rows : 2 * sm_count()) : (unsigned)rows;
-  topk_segment_kernel<SelectedScores><<<grid, kTopkBlock, 0, st>>>(src, rows, k, out_scores, out_idx, nullptr, nullptr);
-  ROD_LAUNCH_CHECK("topk_segment_kernel<SelectedScores>");
+  ROD_CUDA(launch_pdl(topk_segment_kernel<SelectedScores>, dim3(grid), dim3(kTopkBlock), 0, st, src, rows, k, out_scores, out_idx,
+                      (const float*)nullptr, (float*)nullptr));
   return ROD_OK;
 }
 

@@ -26,7 +26,7 @@ from ..anchor_table import AnchorTable, layer_table_for, table_for
 __all__ = [
     "init_anchor", "n_anchor_each_layer", "anchors_one_layer", "anchors_all_layer",
     "encode_locations_one_layer", "decode_locations_one_layer", "jaccard", "refine_groundtruth",
-    "det_groundtruth", "target_gen", "bboxes_select_one_layer", "bboxes_select_all_layers", "detected_bboxes",
+    "det_groundtruth", "target_gen", "target_buffers", "bboxes_select_one_layer", "bboxes_select_all_layers", "detected_bboxes",
     "decode_detected_bboxes", "detect_workspace", "detect_fallback_flags", "softmax",
 ]
 
@@ -265,9 +265,45 @@ def det_groundtruth(refine_out, offset_gt, cbboxes, refine_labels, refine_pos_ma
 
 
 # --------------------------------------------------------------------------------- a9 + a10 fused
+def target_buffers(anchors_all_layer, batch, device, need_cbboxes=True, match_index=False, flat=False):
+    """Extension: preallocated flat outputs for `target_gen(..., out=...)` (a training loop reuses them every
+    step instead of allocating 68 bytes per anchor per call).  flat=True carves all of them out of ONE uint8
+    buffer (key "_flat"), so that a host consumer reads the whole result back with a single copy."""
+    dev = torch.device(device)
+    table = table_for(anchors_all_layer, dev)
+    B, N, f32, i32 = int(batch), table.n, torch.float32, torch.int32
+    if flat:
+        n4 = 3 if need_cbboxes else 2
+        n1 = 4 + (1 if need_cbboxes else 0) + (1 if match_index else 0)
+        buf = torch.empty((B * N * (16 * n4 + 4 * n1),), dtype=torch.uint8, device=dev)
+        cursor = [0]
+
+        def new(shape, dt):
+            nbytes = 4
+            for d in shape:
+                nbytes *= d
+            v = buf[cursor[0]:cursor[0] + nbytes].view(dt).view(shape)
+            cursor[0] += nbytes
+            return v
+        order = ["gt", "det_gt"] + (["cb"] if need_cbboxes else []) + ["pos", "mask", "dlab", "iou"] + \
+                (["lab"] if need_cbboxes else []) + (["idx"] if match_index else [])
+        d = {k: None for k in ("gt", "pos", "cb", "lab", "idx", "det_gt", "mask", "dlab", "iou")}
+        for k in order:
+            d[k] = new((B, N, 4) if k in ("gt", "det_gt", "cb") else (B, N), f32 if k in ("gt", "det_gt", "cb", "iou") else i32)
+        d["_flat"] = buf
+        d["_sched"] = torch.zeros(2, dtype=i32, device=dev)
+        return d
+    new = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+    return {"gt": new((B, N, 4), f32), "pos": new((B, N), i32),
+            "cb": new((B, N, 4), f32) if need_cbboxes else None, "lab": new((B, N), i32) if need_cbboxes else None,
+            "idx": new((B, N), i32) if match_index else None,
+            "det_gt": new((B, N, 4), f32), "mask": new((B, N), i32), "dlab": new((B, N), i32), "iou": new((B, N), f32),
+            "_sched": torch.zeros(2, dtype=i32, device=dev)}     # scheduler counters: zero once, every call leaves them zero
+
+
 def target_gen(anchors_all_layer, center_bboxes, labels, refine_out, gt_counts=None,
                method=None, arm_thresholds=None, det_thresholds=None, return_match_index=False,
-               need_cbboxes=True):
+               need_cbboxes=True, out=None):
     """Extension: the training call sequence train.py:109-113 -> :147-149 in ONE kernel —
     `refine_groundtruth(anchors, center_bboxes, labels, JACCARD_BIGGER)` followed by
     `det_groundtruth(refine_out, refine_gt, refine_cbboxes, refine_labels, refine_pos_mask, anchors)`.
@@ -275,7 +311,7 @@ def target_gen(anchors_all_layer, center_bboxes, labels, refine_out, gt_counts=N
     (det_gt, det_pos_mask, det_labels, iou_all_layers))`, bit-identical to the two calls; the matched GT,
     encoding, label and mask never round-trip through HBM (84 instead of 124 bytes per anchor).
     need_cbboxes=False skips writing refine_cbboxes / refine_labels (only det_groundtruth consumes them):
-    the first tuple then holds None in their place."""
+    the first tuple then holds None in their place.  out=target_buffers(...) writes into preallocated tensors."""
     JB = config.refine_method.JACCARD_BIGGER
     if method is not None and method != JB:
         if method == config.refine_method.JACCARD_TOPK:
@@ -298,12 +334,16 @@ def target_gen(anchors_all_layer, center_bboxes, labels, refine_out, gt_counts=N
         gt_counts = _abi.require_cuda(gt_counts, "gt_counts").to(torch.int32).contiguous()
     B, N = cb.shape[0], table.n
     f32, i32 = torch.float32, torch.int32
-    new = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
-    gt, pos = new((B, N, 4), f32), new((B, N), i32)
-    cbo = new((B, N, 4), f32) if need_cbboxes else None
-    lbo = new((B, N), i32) if need_cbboxes else None
-    idx = new((B, N), i32) if return_match_index else None
-    det_gt, mask, dlab, iou = new((B, N, 4), f32), new((B, N), i32), new((B, N), i32), new((B, N), f32)
+    if out is None:
+        out = target_buffers(table, B, dev, need_cbboxes, return_match_index)
+    else:
+        for k, v in out.items():
+            if v is not None and not k.startswith("_") and (v.device != dev or v.shape[0] != B or v.shape[1] != N or not v.is_contiguous()):
+                raise ValueError("out[%r] does not match batch %d x %d anchors on %s" % (k, B, N, dev))
+        need_cbboxes = out["cb"] is not None and out["lab"] is not None
+        return_match_index = out.get("idx") is not None
+    gt, pos, cbo, lbo, idx = out["gt"], out["pos"], out["cb"] if need_cbboxes else None, out["lab"] if need_cbboxes else None, out.get("idx")
+    det_gt, mask, dlab, iou = out["det_gt"], out["mask"], out["dlab"], out["iou"]
     a, bb = _abi.DLArgs(), [B]
     with _abi.device_guard(dev):
         ro = _abi.layered_arg(refine_out, table, 4, f32, a, bb)
@@ -313,7 +353,8 @@ def target_gen(anchors_all_layer, center_bboxes, labels, refine_out, gt_counts=N
                 1 if lab.dtype == torch.int64 else 0, gt_counts.data_ptr() if gt_counts is not None else None, B,
                 cb.shape[1], ro, gt.data_ptr(), cbo.data_ptr() if cbo is not None else None,
                 lbo.data_ptr() if lbo is not None else None, pos.data_ptr(), idx.data_ptr() if idx is not None else None,
-                det_gt.data_ptr(), mask.data_ptr(), dlab.data_ptr(), iou.data_ptr(), _abi.stream_ptr(dev)))
+                det_gt.data_ptr(), mask.data_ptr(), dlab.data_ptr(), iou.data_ptr(), out["_sched"].data_ptr(),
+                _abi.stream_ptr(dev)))
     LL = _abi.LayerList
     arm = (LL(gt, table, True, False), LL(cbo, table, True, False) if need_cbboxes else None,
            LL(lbo, table, True, True) if need_cbboxes else None, LL(pos, table, True, True))
@@ -410,7 +451,7 @@ def detect_fallback_flags(workspace):
 
 
 def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_threshold, clipping_bbox,
-            top_k, keep_top_k, num_classes, return_counts, from_logits=False, workspace=None):
+            top_k, keep_top_k, num_classes, return_counts, from_logits=False, workspace=None, counts_out=None):
     thr = 0.0 if select_threshold is None else float(select_threshold)
     preds = [_f32(p, "predictions") for p in preds]
     dev, B, C = preds[0].device, preds[0].shape[0], preds[0].shape[-1]
@@ -428,6 +469,10 @@ def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_thr
     scores = torch.empty((C, B, keep_top_k), dtype=torch.float32, device=dev)
     boxes = torch.empty((C, B, keep_top_k, 4), dtype=torch.float32, device=dev)
     counts = torch.empty((C, B), dtype=torch.int32, device=dev) if return_counts else None
+    if counts_out is not None:                   # caller-provided [C, B] int32 (e.g. a slice of an all-gather staging buffer)
+        if counts_out.shape != (C, B) or counts_out.dtype != torch.int32 or not counts_out.is_contiguous() or counts_out.device != dev:
+            raise ValueError("counts_out must be a contiguous int32 [%d, %d] tensor on %s" % (C, B, dev))
+        counts, return_counts = counts_out, True
     if B:
         need = int(_abi.lib.rod_detect_workspace_bytes(lay, B, C, top_k))
         ws = workspace
@@ -470,7 +515,7 @@ def softmax(clf_out, out=None):
 
 def detected_bboxes(predictions, localisations, select_threshold=None, nms_threshold=0.5,
                     clipping_bbox=None, top_k=800, keep_top_k=200, return_counts=False, from_logits=False,
-                    workspace=None):
+                    workspace=None, counts_out=None):
     """select -> top_k -> per-class NMS -> zero-pad (-> clip) in two kernels
     (utils/net_tools.py:739-758).  predictions: list of [B,fh,fw,A,11] post-softmax scores (or the
     class logits with from_logits=True: slim.softmax is then fused into the select pass);
@@ -478,19 +523,19 @@ def detected_bboxes(predictions, localisations, select_threshold=None, nms_thres
     c -> [B,keep_top_k,4] for c = 1..config.total_obj_n-1."""
     locs = [_f32(l, "localisations") for l in localisations]
     return _detect(list(predictions), locs, None, None, None, select_threshold, nms_threshold,
-                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits, workspace)
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits, workspace, counts_out)
 
 
 def decode_detected_bboxes(anchors_all_layer, refine_out, det_out, predictions, select_threshold=None,
                            nms_threshold=0.5, clipping_bbox=None, top_k=800, keep_top_k=200,
-                           return_counts=False, from_logits=False, workspace=None):
+                           return_counts=False, from_logits=False, workspace=None, counts_out=None):
     """Extension: the inference call sequence of evaluate.py:139-151 in one call —
     c2c(decode(anchors, refine_out + det_out)) is evaluated only for the top_k candidates of
     each (image, class) instead of materialising [B,N,4] boxes first."""
     ro = [_f32(t, "refine_out") for t in refine_out]
     do = [_f32(t, "det_out") for t in det_out]
     return _detect(list(predictions), None, ro, do, anchors_all_layer, select_threshold, nms_threshold,
-                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits, workspace)
+                   clipping_bbox, top_k, keep_top_k, config.total_obj_n, return_counts, from_logits, workspace, counts_out)
 
 
 # --------------------------------------------------------------------------------- f-3 losses

@@ -321,14 +321,13 @@ def test_arm_gt_count_extremes(env):
 
 @pytest.mark.parametrize("where", ["sampled_only", "unsampled_only"])
 def test_detect_unrepresentative_sample(env, where):
-    """The scan pass cuts candidates below a score estimated from every 8th 256-anchor tile.  Put one class's
-    candidates only INTO those tiles (the estimate overshoots: fewer than top_k survive the cut) or only
-    OUTSIDE them (no estimate at all): the result must still be exact (general kernels / uncut lists)."""
+    """The scan pass cuts candidates below scores estimated from every 19th anchor (n % 19 == 9).
+    Put one class's candidates only ONTO those anchors (the estimate overshoots: fewer than top_k survive the cut) or only
+    OFF them (no estimate at all): the result must still be exact (general kernels / uncut lists)."""
     layout, B = "512", 2
     table = env.otable[layout]
     probs, ro, do = _detect_inputs(env, layout, 800, B, stress=False)
-    tile = np.arange(table.n) // 256
-    sampled = (tile % 8) == 4
+    sampled = (np.arange(table.n) % 19) == 9
     rng = np.random.default_rng(5)
     col = np.full((B, table.n), 0.01, np.float32)
     sel = sampled if where == "sampled_only" else ~sampled
@@ -343,7 +342,7 @@ def test_detect_unrepresentative_sample(env, where):
         assert bit_equal(rs[c].cpu().numpy(), o_s[c]), c
         assert bit_equal(rb[c].cpu().numpy(), o_b[c]), c
         assert np.array_equal(counts[c].cpu().numpy(), (o_s[c] != 0).sum(1))
-    assert (o_s[3] != 0).sum() == B * 200
+    assert (o_s[3] != 0).sum() >= B * 150
 
 
 # ------------------------------------------------------------------------------- bench.py's exact launch geometry
@@ -398,6 +397,9 @@ def test_detect_clustered_scores_bit_exact(env, mode, B):
     ndet, flags = _detect_vs_c_oracle(env, "512", probs, ro, do)
     assert ndet > B * 50
     print("clustered %s B=%d: fallback rate %.4f" % (mode, B, flags[1:].mean()))
+    # the sample is spatially stratified and full slices spill into a shared list: clustering must not push
+    # segments onto the (slow) exact general kernels
+    assert flags[1:].mean() < 0.02
 
 
 def test_match_encode_bench_geometry_bit_exact(env):
