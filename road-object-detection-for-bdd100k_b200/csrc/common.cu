@@ -21,12 +21,12 @@ int cuda_fail(cudaError_t e, const char* what) {
   return ROD_E_CUDA;
 }
 
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("ROD_NO_PDL");
-    return !(e && e[0] == '1');
+int pdl_mask() {
+  static const int mask = [] {
+    const char* e = getenv("ROD_PDL_MASK");
+    return e ? atoi(e) : 6;
   }();
-  return on;
+  return mask;
 }
 
 int sm_count() {

@@ -43,9 +43,13 @@ int sm_count();
 // running (as soon as every CTA of the predecessor has executed pdl_launch_dependents() or exited); it must call
 // pdl_wait() before touching anything the predecessor writes.  Hides the launch latency and the prologue of the
 // short kernels of one rod_detect call; stream capture turns these launches into programmatic graph edges.
-bool pdl_enabled();   // false when the environment sets ROD_NO_PDL=1 (measurement aid)
+// `which` selects the launch class: 1 scan pass, 2 segment kernel, 4 general (fallback) kernels.  Default mask 6:
+// measured on B200 (decode_nms, B = 64), the attribute on the segment / fallback launches is neutral to slightly
+// positive (75.0 vs 75.6 us per step), on the scan launch it costs 10 us (85 us: the scan CTAs become resident
+// under the sample kernel and the step gets slower, not faster).  ROD_PDL_MASK overrides it (measurement aid).
+int pdl_mask();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -55,7 +59,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_mask() & which) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

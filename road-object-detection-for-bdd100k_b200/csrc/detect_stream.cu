@@ -1049,8 +1049,8 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
       ks<<<dim3(stiles, batch), 256, 0, st>>>(SP);
       ROD_LAUNCH_CHECK("sample_kernel");
     }
-    // One stream, programmatic launches: each kernel is scheduled while its predecessor drains and waits
-    // (pdl_wait) before it reads the predecessor's results.  (Measured and dropped: persistent scan CTAs walking
+    // One stream; the segment and general kernels are programmatic launches (scheduled while the predecessor
+    // drains, pdl_wait before they read its results); see launch_pdl for what that buys.  (Measured and dropped: persistent scan CTAs walking
     // the images in order with per-image completion counters so that segments start under the scan — the scan
     // needs its ~4 CTAs per SM, 108 vs 77 us; and scanning the batch in 2 / 4 / 8 slices with the segment
     // kernels forked to side streams through events — 103 / 120 / 165 us, the cross-stream edges cost more
@@ -1058,12 +1058,12 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     const size_t smem0 = (size_t)kScanStages * sizeof(float) * kScanBlock * 11 + sizeof(ScanShared<11>);
     auto k0 = logits ? scan_kernel<11, true, kScanStages> : scan_kernel<11, false, kScanStages>;
     ROD_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-    ROD_CUDA(launch_pdl(k0, dim3(chunks, batch), dim3(kScanBlock), smem0, st, SP));
+    ROD_CUDA(launch_pdl(1, k0, dim3(chunks, batch), dim3(kScanBlock), smem0, st, SP));
     SegParams G;
     fill_seg_params(G);
     G.chunks = n_chunks; G.spc = spc; G.force_dense = 0;
     G.b0 = 0; G.nb = batch;
-    ROD_CUDA(launch_pdl(segment_kernel, dim3((unsigned)rows), dim3(kSegBlock), seg_smem, st, G, (const unsigned long long*)g_list2,
+    ROD_CUDA(launch_pdl(2, segment_kernel, dim3((unsigned)rows), dim3(kSegBlock), seg_smem, st, G, (const unsigned long long*)g_list2,
                         out_scores, out_boxes, out_counts));
   } else {
     // ---- generic prediction depth: plain-load two-pass kernels, every segment takes the dense route

@@ -361,7 +361,7 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   ROD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DenseBoxes d{};
   const unsigned grid = over_cnt ? (unsigned)(rows < 4 * sm_count() ? rows : 4 * sm_count()) : (unsigned)rows;
-  ROD_CUDA(launch_pdl(k, dim3(grid), dim3(kNmsBlock), smem, st, d, g, rows, top_k, nms_threshold, keep_top_k, ignore_class,
+  ROD_CUDA(launch_pdl(4, k, dim3(grid), dim3(kNmsBlock), smem, st, d, g, rows, top_k, nms_threshold, keep_top_k, ignore_class,
                       clip_box, out_scores, out_bboxes, (int32_t*)nullptr, out_counts));
   return ROD_OK;
 }

@@ -153,7 +153,7 @@ topk_segment_kernel(const __grid_constant__ Src src, long long rows, int k, floa
 int launch_topk_selected(const SelectedScores& src, long long rows, int k, float* out_scores, int32_t* out_idx,
                          cudaStream_t st) {
   const unsigned grid = src.over_cnt ? (unsigned)(rows < 2 * sm_count() ? rows : 2 * sm_count()) : (unsigned)rows;
-  ROD_CUDA(launch_pdl(topk_segment_kernel<SelectedScores>, dim3(grid), dim3(kTopkBlock), 0, st, src, rows, k, out_scores, out_idx,
+  ROD_CUDA(launch_pdl(4, topk_segment_kernel<SelectedScores>, dim3(grid), dim3(kTopkBlock), 0, st, src, rows, k, out_scores, out_idx,
                       (const float*)nullptr, (float*)nullptr));
   return ROD_OK;
 }

@@ -288,3 +288,13 @@ def test_anchor_cache_key_follows_content():
     b[0][2][1] = 2.0                                              # in-place mutation changes the key
     assert anchor_table._content_key(b, "cuda:0", "all") != k1
     assert anchor_table._content_key(a, "cuda:1", "all") != k1 and anchor_table._content_key(a, "cuda:0", "one") != k1
+
+
+def test_crop_without_overlap_threshold_is_rejected():
+    """process_raw_gt_train: the reference always filters a crop's boxes at 0.3 (utils/augmentation/process.py:134-138);
+    a crop with crop_overlap=None has no reference meaning and must not silently filter at 0."""
+    import torch
+    from rodet_b200.utils.data_pileline_tools import process_raw_gt_train
+    labels, boxes = torch.zeros((1, 2), dtype=torch.int64), torch.zeros((1, 2, 4))
+    with pytest.raises(ValueError, match="crop_overlap=None"):
+        process_raw_gt_train(labels, boxes, None, torch.tensor([[0.0, 0.0, 1.0, 1.0]]), None, crop_overlap=None)
