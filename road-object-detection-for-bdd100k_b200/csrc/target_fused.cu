@@ -38,8 +38,10 @@ struct FusedParams {
   unsigned* sched;                      // [0] next work item, [1] CTAs that have left
 };
 
+// (10 resident CTAs per SM asked of the compiler = 47 registers: 36.9 us at B = 32; 8 / 12 / 14 CTAs measured 38.5 /
+// 37.3 / 40.3 us — the kernel is bound by its instruction count, not by occupancy)
 template <typename LabelT>
-__global__ void __launch_bounds__(kTfBlock)
+__global__ void __launch_bounds__(kTfBlock, 10)
 target_fused_kernel(const __grid_constant__ FusedParams P) {
   extern __shared__ float4 s_box[];                         // [gmax] GT corners (net_tools.py:323)
   float* s_area = reinterpret_cast<float*>(s_box + P.gmax);  // [gmax] GT areas (:265)
