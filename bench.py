@@ -217,7 +217,7 @@ def cpu_baselines(args, B_m, B_d):
     v_11, n_11 = cp.time_images(cp.detect, one, 1, sec * 0.1, 200)
     v_m1, _ = cp.time_images(cp.match_encode, lambda i: host_inputs_match(cp.synth, 930_000 + i, 1), 1, sec * 0.1, 200)
     cp.C.set_threads(threads)
-    note = "C/OpenMP port of the reference path (oracle/c); TF-1 reference cannot run here"
+    note = "C/OpenMP port (oracle/c); TF-1 reference cannot run here"
     return {
         "match_encode": {"value": v_m, "unit": "images/s", "cores": t, "kind": "port",
                          "sample": "%d images in batches of %d on %d threads; %s" % (n_m, B_m, t, note)},
@@ -283,7 +283,7 @@ def run_reference(args):
             line["%s_e2e_value" % name] = v2
             line["%s_ms_per_step" % name] = ms2
             line["%s_batch_per_gpu" % name] = B2
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(w):
@@ -477,8 +477,7 @@ def bench_match(G, table, B, extras):
         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "moved_bytes_per_launch": real,
         "launch_ms": t1["ms_per_step"], "frac_fp32_nofma": frac_fp32, "fp32_nofma_tops_measured": fp32_tops,
         "pair_flops_per_launch": pair_flops,
-        "note": "one launch = one step (B images); algorithmic bytes = SURVEY 8d M total (124 N + 20 G per image), the "
-                "fused kernel moves 84 N + 20 G; the all-pairs FP32 bound (14 N G flops, no FMA) binds about equally"}
+        "note": "1 launch = 1 step; algorithmic = SURVEY 8d M (124N+20G B/img), moved = 84N+20G; FP32 no-FMA pair bound (14NG flops) beside it"}
     if extras:
         t4 = G.time_loops(runner(fused, args.streams), K)
         t2 = G.time_loops(runner(two_call), K)
@@ -490,8 +489,8 @@ def bench_match(G, table, B, extras):
     res["config"] = {"workload": workload_name("match_encode"), "batch_per_gpu": B, "global_batch": B * G.world,
                      "image": "512x512", "anchors": N, "max_gt": 100, "mean_gt": mean_g,
                      "api": "net_tools.target_gen (fused ARM+ODM kernel)",
-                     "l2": "inputs larger than L2: %d rotating input/output sets of ~100 MB" % n_sets,
-                     "launch": "python launches" if args.no_graphs else "CUDA graph of %d serial steps per host launch, one batch in flight" % K,
+                     "l2": "inputs > L2: %d rotating sets of ~100 MB" % n_sets,
+                     "launch": "python launches" if args.no_graphs else "CUDA graph of %d serial steps, one batch in flight" % K,
                      "parallelism": "image-sharded, no collective"}
     return res
 
@@ -558,7 +557,7 @@ def e2e_match(G, table, B, s0, extras):
     res = {"value": G.world * B / (t["ms_per_step"] * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": t["ms_per_step"],
            "h2d_GBps_per_rank": h2d / (t["ms_per_step"] * 1e-3) / 1e9, "d2h_GBps_per_rank": d2h / (t["ms_per_step"] * 1e-3) / 1e9,
-           "api": "net_tools.target_gen on pinned host inputs (1 H2D copy), all 8 output lists read back (1 D2H copy), 2 batches in flight"}
+           "api": "target_gen from pinned host inputs (1 H2D copy), all 8 output lists read back (1 D2H copy), 2 batches in flight"}
     if extras:
         mask = make_step(False)
         t2 = G.time_loops(lambda: run(mask, K), K, min_ms=40.0, warm_loops=1, max_loops=20)
@@ -705,8 +704,28 @@ def flat(line, prefix, r, keys=("value", "ms_per_step", "value_overlapped", "ms_
         line["%s_batch_per_gpu" % prefix] = r["config"]["batch_per_gpu"]
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything any library prints to fd 1 (NCCL's version banner, ...) goes to stderr; the one JSON line is written
+    to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -759,7 +778,7 @@ def main():
             line["match_encode_cpu_value"] = cb["match_encode"]["value"]
         line["cpu_config0"] = cb["config0"]
     if G.rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if G.world > 1:
         G.dist.destroy_process_group()
 

@@ -328,6 +328,35 @@ int rod_gt_boxes_update(const float* bboxes, const void* labels, int labels_i64,
                         int filter_overlap, float threshold, int assign_negative, int clamp01,
                         float* out_bboxes, void* out_labels, int32_t* out_counts, void* stream);
 
+/* ---- f-4  ground truth from the on-disk format --------------------------------------
+ * The reference stores one tf.train.Example per image in TFRecord files (writer
+ * dataset/pascalvoc_to_tfrecords.py:128-170, schema dataset/pascalvoc_common.py:75-98) and reads
+ * them through slim's DatasetDataProvider (utils/data_pileline_tools.py:33-71).  These calls
+ * replace the ground-truth half of that reader: a HOST parser of the file bytes (image decoding is
+ * out of scope) and a device gather that assembles padded batches.
+ *   rod_tfrecord_index   : counts the records and their objects (`data` = n_bytes of one or more
+ *                          concatenated TFRecord files in host memory; verify_crc checks the masked
+ *                          CRC-32C of every record).
+ *   rod_tfrecord_read_gt : fills host arrays — ymin/xmin/ymax/xmax[n_objects] float32 (the
+ *                          'image/object/bbox/{ymin,...}' features), label/difficult/truncated[n_objects]
+ *                          int64 (difficult / truncated may be NULL), offsets[n_records + 1] (objects
+ *                          of record r = [offsets[r], offsets[r+1])), shape[n_records][3] (may be NULL).
+ *   rod_gt_gather        : DEVICE arrays (the ones above, uploaded once) + indices[batch] (record per
+ *                          image; NULL = 0..batch-1) -> bboxes[batch][gmax][4] corner form
+ *                          (ymin,xmin,ymax,xmax), labels[batch][gmax], difficults[batch][gmax] (may be
+ *                          NULL), counts[batch] = min(#objects, gmax); rows zero padded.  This is the
+ *                          input form of rod_gt_boxes_update / rod_corner_to_center / rod_arm_match_encode. */
+int rod_tfrecord_index(const void* data, size_t n_bytes, int verify_crc, int64_t* n_records,
+                       int64_t* n_objects);
+int rod_tfrecord_read_gt(const void* data, size_t n_bytes, int verify_crc, int64_t n_records,
+                         int64_t n_objects, float* ymin, float* xmin, float* ymax, float* xmax,
+                         int64_t* label, int64_t* difficult, int64_t* truncated, int64_t* offsets,
+                         int64_t* shape);
+int rod_gt_gather(const float* ymin, const float* xmin, const float* ymax, const float* xmax,
+                  const int64_t* label, const int64_t* difficult, const int64_t* offsets,
+                  const int64_t* indices, int batch, int gmax, float* bboxes, int64_t* labels,
+                  int64_t* difficults, int32_t* counts, void* stream);
+
 /* ---- measurement helpers (bench.py) ------------------------------------------------
  * rod_peak_fp32_nofma: runs a dependent-chain FADD/FMUL (no FMA) kernel and returns in
  * *ops the number of FP32 instructions-lanes issued; time it with events on `stream`. */

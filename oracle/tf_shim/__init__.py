@@ -525,6 +525,10 @@ def _build_tf_module():
     image.non_max_suppression = non_max_suppression
     tf.image = image
 
+    # tf.train.Example & co., tf.python_io.TFRecordWriter, tf.gfile: the dataset converter (dataset/pascalvoc_to_tfrecords.py)
+    from . import example_proto
+    example_proto.attach(tf)
+
     # anything else (tf.contrib, tf.app, tf.summary, tf.GraphKeys, ...) is
     # imported-but-not-executed on the hot path: hand out mocks.
     def __getattr__(name):

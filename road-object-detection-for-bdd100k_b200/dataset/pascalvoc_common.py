@@ -1,0 +1,110 @@
+"""Ground truth from the reference's on-disk format.
+
+The reference writes one `tf.train.Example` per image into TFRecord files (dataset/pascalvoc_to_tfrecords.py:128-170)
+and reads them back with slim's `DatasetDataProvider` over the schema of dataset/pascalvoc_common.py:75-98
+(`get_split`), feeding `object/bbox` ([ymin, xmin, ymax, xmax]), `object/label` and `object/difficult` to
+prepare_data_train / prepare_data_test (utils/data_pileline_tools.py:33-71).  Here the box-level fields of ALL records
+are parsed once by the native reader (csrc/tfrecord.cu), uploaded to the GPU once, and every batch is assembled on
+the device (`rod_gt_gather`) into the padded form the rest of the path takes:
+
+    gt = read_ground_truth(glob('bdd100k_train_*.tfrecord'))           # host, once
+    dgt = gt.to('cuda')                                                # HBM, once (BDD100K: ~40 MB)
+    bboxes, labels, difficults, counts = dgt.batch(indices)            # device, per step
+    center = cornerBboxes_2_centerBboxes(bboxes); refine_groundtruth(anchors, center, labels, ..., gt_counts=counts)
+
+Image bytes ('image/encoded') are skipped: JPEG decoding and augmentation are outside the box-level path."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _abi
+
+# the keys this reader consumes (dataset/pascalvoc_common.py:82-97)
+BBOX_KEYS = ('image/object/bbox/ymin', 'image/object/bbox/xmin', 'image/object/bbox/ymax', 'image/object/bbox/xmax')
+LABEL_KEY, DIFFICULT_KEY, TRUNCATED_KEY, SHAPE_KEY = ('image/object/bbox/label', 'image/object/bbox/difficult',
+                                                      'image/object/bbox/truncated', 'image/shape')
+
+
+class GroundTruth:
+    """Ragged ground truth of a dataset: per object ymin/xmin/ymax/xmax (float32), label/difficult/truncated (int64);
+    `offsets[r] : offsets[r+1]` are the objects of record r; `shape[r]` = (height, width, channels)."""
+
+    def __init__(self, ymin, xmin, ymax, xmax, label, difficult, truncated, offsets, shape):
+        self.ymin, self.xmin, self.ymax, self.xmax = ymin, xmin, ymax, xmax
+        self.label, self.difficult, self.truncated, self.offsets, self.shape = label, difficult, truncated, offsets, shape
+
+    def __len__(self):
+        return int(self.offsets.shape[0]) - 1
+
+    @property
+    def max_objects(self):
+        d = np.diff(self.offsets) if isinstance(self.offsets, np.ndarray) else (self.offsets[1:] - self.offsets[:-1])
+        return int(d.max()) if len(self) else 0
+
+    def to(self, device):
+        """Upload once; `batch()` then runs entirely on the device."""
+        dev = torch.device(device)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev) if isinstance(a, np.ndarray) else a.to(dev)
+        g = GroundTruth(*[t(a) for a in (self.ymin, self.xmin, self.ymax, self.xmax, self.label, self.difficult,
+                                         self.truncated, self.offsets, self.shape)])
+        g._max = self.max_objects
+        return g
+
+    def batch(self, indices=None, max_gt=None, batch=None):
+        """Padded batch on the device: (bboxes [B,G,4] float32 corner form, labels [B,G] int64, difficults [B,G] int64,
+        counts [B] int32).  `indices`: int64 tensor / sequence of record numbers (None: records 0..batch-1);
+        G = max_gt (default: the largest object count of the dataset); rows are zero padded, counts clipped to G."""
+        if not isinstance(self.offsets, torch.Tensor) or not self.offsets.is_cuda:
+            raise ValueError("call .to('cuda') first: batches are assembled on the device (there is no CPU path)")
+        dev = self.offsets.device
+        if indices is not None:
+            idx = torch.as_tensor(indices, dtype=torch.int64, device=dev).contiguous()
+            if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= len(self)):
+                raise IndexError("record index out of range")
+            B = int(idx.numel())
+        else:
+            idx, B = None, len(self) if batch is None else int(batch)
+            if B > len(self):
+                raise IndexError("batch exceeds the number of records")
+        G = int(max_gt) if max_gt is not None else max(1, getattr(self, "_max", 1))
+        bboxes = torch.empty((B, G, 4), dtype=torch.float32, device=dev)
+        labels = torch.empty((B, G), dtype=torch.int64, device=dev)
+        diff = torch.empty((B, G), dtype=torch.int64, device=dev)
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        P = lambda t: t.data_ptr() if t is not None and t.numel() else None
+        with _abi.device_guard(dev):
+            _abi.check(_abi.lib.rod_gt_gather(P(self.ymin), P(self.xmin), P(self.ymax), P(self.xmax), P(self.label),
+                                              P(self.difficult), self.offsets.data_ptr(), P(idx), B, G, bboxes.data_ptr(),
+                                              labels.data_ptr(), diff.data_ptr(), counts.data_ptr(), _abi.stream_ptr(dev)))
+        return bboxes, labels, diff, counts
+
+
+def read_ground_truth(files, verify_crc=True):
+    """Parses the ground-truth features of every record of one or more TFRecord files (paths, or bytes objects) with the
+    native reader.  Raises ValueError on corrupted / malformed records.  Returns a host `GroundTruth` (NumPy arrays)."""
+    if isinstance(files, (str, bytes, bytearray, memoryview)):
+        files = [files]
+    parts = []
+    for f in files:
+        if isinstance(f, str):
+            with open(f, "rb") as fh:
+                parts.append(fh.read())
+        else:
+            parts.append(bytes(f))
+    data = b"".join(parts)                      # TFRecord files concatenate
+    buf = ctypes.create_string_buffer(data, len(data)) if data else None
+    ptr = ctypes.addressof(buf) if buf is not None else None
+    n_rec, n_obj = ctypes.c_int64(0), ctypes.c_int64(0)
+    _abi.check(_abi.lib.rod_tfrecord_index(ptr, len(data), 1 if verify_crc else 0, ctypes.byref(n_rec), ctypes.byref(n_obj)))
+    R, O = n_rec.value, n_obj.value
+    f32 = lambda: np.zeros(O, dtype=np.float32)
+    i64 = lambda: np.zeros(O, dtype=np.int64)
+    ymin, xmin, ymax, xmax, label, difficult, truncated = f32(), f32(), f32(), f32(), i64(), i64(), i64()
+    offsets, shape = np.zeros(R + 1, dtype=np.int64), np.zeros((R, 3), dtype=np.int64)
+    p = lambda a: a.ctypes.data if a.size else None
+    _abi.check(_abi.lib.rod_tfrecord_read_gt(ptr, len(data), 0, R, O, p(ymin), p(xmin), p(ymax), p(xmax), p(label), p(difficult),
+                                             p(truncated), offsets.ctypes.data, p(shape)))
+    return GroundTruth(ymin, xmin, ymax, xmax, label, difficult, truncated, offsets, shape)

@@ -91,3 +91,45 @@ def test_random_batch_into_arm(env):
             continue
         o = R.arm_match_encode(table, R.corner_to_center(g_b[b, :k]), g_l[b, :k])
         assert np.array_equal(gpos[b], o[3]) and np.array_equal(gidx[b], o[4])
+
+
+def test_tfrecord_ground_truth_batches_on_device(env):
+    """f-4: records written by the reference converter -> native reader -> device-resident ragged arrays -> padded batches
+    assembled by rod_gt_gather -> straight into the box chain and ARM matching."""
+    import os
+    from conftest import GOLDEN
+    from rodet_b200.dataset.pascalvoc_common import read_ground_truth
+    z = golden("voc_gt_expected.npz")
+    gt = read_ground_truth(os.path.join(GOLDEN, "voc_gt_000.tfrecord"))
+    dgt = gt.to(env.dev)
+    idx = [7, 0, 5, 11, 3]                                              # record 5 has no objects
+    bboxes, labels, diff, counts = dgt.batch(idx)
+    G = int(np.diff(z["offsets"]).max())
+    assert bboxes.shape == (5, G, 4) and labels.shape == (5, G) and counts.dtype == torch.int32
+    b_np, l_np, c_np = bboxes.cpu().numpy(), labels.cpu().numpy(), counts.cpu().numpy()
+    for row, r in enumerate(idx):
+        o0, o1 = int(z["offsets"][r]), int(z["offsets"][r + 1])
+        g = o1 - o0
+        assert c_np[row] == g
+        exp = np.stack([z["ymin"][o0:o1], z["xmin"][o0:o1], z["ymax"][o0:o1], z["xmax"][o0:o1]], 1)
+        assert bit_equal(b_np[row, :g], exp) and np.array_equal(l_np[row, :g], z["label"][o0:o1])
+        assert not b_np[row, g:].any() and not l_np[row, g:].any()
+    assert not diff.any()
+    # clipped to max_gt, and the default index range
+    b2, l2, _, c2 = dgt.batch(max_gt=4, batch=3)
+    assert b2.shape == (3, 4, 4) and c2.tolist() == [min(4, int(z["offsets"][r + 1] - z["offsets"][r])) for r in range(3)]
+    with pytest.raises(IndexError):
+        dgt.batch([12])
+    with pytest.raises(ValueError):
+        gt.batch([0])                                                   # host arrays: no CPU path
+    # into the pipeline: clamp chain -> centre form -> ARM (images without objects give all-zero targets)
+    ol, ob, oc = env.dp.process_raw_gt_train(labels, bboxes, counts)
+    center = env.ct.cornerBboxes_2_centerBboxes(ob)
+    anchors = golden_anchors("418")
+    out = env.nt.refine_groundtruth(anchors, center, ol, env.config.refine_method.JACCARD_BIGGER, gt_counts=oc)
+    pos = np.concatenate([p.cpu().numpy().reshape(5, -1) for p in out[3]], axis=1)
+    assert pos[2].sum() == 0 and pos[0].sum() > 0
+    table = R.AnchorTable(anchors)
+    k = int(oc[0])
+    o = R.arm_match_encode(table, R.corner_to_center(ob[0, :k].cpu().numpy()), ol[0, :k].cpu().numpy())
+    assert np.array_equal(pos[0], o[3])
