@@ -56,7 +56,7 @@ def run(device="cuda:0", batch=4, first_image=0):
                                                  det_gt, det_pos_mask, det_labels, iou_all_layers)))
     return {"per_image_equals_batched": bool(same), "fused_equals_two_calls": bool(fused_same),
             "arm_positives": int(sum(int(m.sum()) for m in refine_pos_mask)), "odm_positives": int(sum(int(m.sum()) for m in det_pos_mask)),
-            "refine_loss": float(refine_loss), "det_loss": float(det_loss), "clf_loss": float(clf_loss),
+            "refine_loss": float(refine_loss.detach()), "det_loss": float(det_loss.detach()), "clf_loss": float(clf_loss.detach()),
             "grad_norm_refine": float(sum(t.grad.norm() ** 2 for t in refine_out) ** 0.5)}
 
 

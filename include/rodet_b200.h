@@ -284,6 +284,13 @@ int rod_tpfp_append(const float* scores, const uint8_t* tp, const uint8_t* fp, i
                     const int64_t* num_gbboxes, int n_gb, int remove_zero_scores, float rm_threshold,
                     int64_t id_base, float* v_scores, uint8_t* v_tp, uint8_t* v_fp, int64_t* v_ids,
                     int64_t capacity, int64_t* v_count, int64_t* v_nobjects, void* stream);
+/* rod_sort_scores_desc replaces the sort in front of it: tf.nn.top_k(scores, k, sorted=True) + gather
+ * (utils/tf_extended/metrics.py:117-123): the k best of n scores in descending order, equal scores in index
+ * order; emits any of tp_sorted / fp_sorted (uint8), scores_sorted, idx_sorted (NULL to skip). */
+size_t rod_sort_scores_workspace_bytes(int64_t n);
+int rod_sort_scores_desc(const float* scores, int64_t n, int64_t k, const uint8_t* tp, const uint8_t* fp,
+                         uint8_t* tp_sorted, uint8_t* fp_sorted, float* scores_sorted,
+                         int32_t* idx_sorted, void* workspace, size_t workspace_bytes, void* stream);
 size_t rod_precision_recall_workspace_bytes(int64_t n);
 int rod_precision_recall(const uint8_t* tp_sorted, const uint8_t* fp_sorted, int64_t n,
                          const int64_t* num_gbboxes, double* precision, double* recall,

@@ -73,6 +73,8 @@ SIGNATURES = {
     "rod_dl_detect_logits": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_dl_softmax": (_i, [_vp, _vp, _vp]),
     "rod_tpfp_append": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _i, _i, _f, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "rod_sort_scores_workspace_bytes": (_sz, [_i64]),
+    "rod_sort_scores_desc": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_precision_recall_workspace_bytes": (_sz, [_i64]),
     "rod_precision_recall": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_average_precision": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -127,9 +127,18 @@ def precision_recall(num_gbboxes, num_detections, tp, fp, scores, dtype=torch.fl
     k = int(num_detections)
     if k > scores.numel():
         raise ValueError("num_detections=%d exceeds the %d scores (tf.nn.top_k)" % (k, scores.numel()))
-    _, idx = torch.sort(scores, descending=True, stable=True)            # tf.nn.top_k(scores, k, sorted=True)
-    idx = idx[:k]
-    tp_s, fp_s = _u8(tp.reshape(-1)[idx]), _u8(fp.reshape(-1)[idx])
+    # tf.nn.top_k(scores, k, sorted=True) + gather of tp / fp (:117-123): the library's own bitonic sort on
+    # (score desc, index asc) composite keys, gather fused into its last pass
+    scores = scores.to(torch.float32).contiguous()
+    tp_u, fp_u = _u8(tp.reshape(-1)).contiguous(), _u8(fp.reshape(-1)).contiguous()
+    tp_s, fp_s = torch.empty(k, dtype=torch.uint8, device=dev), torch.empty(k, dtype=torch.uint8, device=dev)
+    if k:
+        nbs = int(_abi.lib.rod_sort_scores_workspace_bytes(scores.numel()))
+        wss = torch.empty(nbs, dtype=torch.uint8, device=dev)
+        with _abi.device_guard(dev):
+            _abi.check(_abi.lib.rod_sort_scores_desc(scores.data_ptr(), scores.numel(), k, tp_u.data_ptr(), fp_u.data_ptr(),
+                                                     tp_s.data_ptr(), fp_s.data_ptr(), None, None, wss.data_ptr(), nbs,
+                                                     _abi.stream_ptr(dev)))
     ngb = torch.as_tensor(num_gbboxes, device=dev).to(torch.int64).reshape(1).contiguous()
     precision = torch.empty(k, dtype=torch.float64, device=dev)
     recall = torch.empty(k, dtype=torch.float64, device=dev)

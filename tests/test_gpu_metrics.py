@@ -141,3 +141,31 @@ def test_end_to_end_eval_chain(tfe):
     mAP = torch.stack(aps).sum() / len(aps)                # evaluate.py:184-185  tf.add_n(aps) / len(aps)
     assert 0.0 <= float(mAP) <= 1.0
     tfe.reset_local_variables()
+
+
+@pytest.mark.parametrize("n", [1, 7, 2048, 2049, 5000, 70001])
+def test_score_sort_matches_top_k_order(cuda_device, n):
+    """rod_sort_scores_desc (the library's own sort behind precision_recall): descending score, equal scores in
+    index order = tf.nn.top_k(scores, k, sorted=True) (utils/tf_extended/metrics.py:117-123); NumPy stable argsort is
+    the oracle.  Heavy ties (scores quantised to 1/64) and -0.0 / +0.0 included."""
+    import ctypes
+    from rodet_b200 import _abi
+    rng = np.random.default_rng(n)
+    scores = (np.round(rng.uniform(0, 1, n) * 64) / 64).astype(np.float32)
+    scores[rng.uniform(size=n) < 0.05] = np.float32(-0.0)
+    tp = (rng.uniform(size=n) < 0.4).astype(np.uint8)
+    fp = (1 - tp).astype(np.uint8)
+    order = np.argsort(-(scores + np.float32(0.0)), kind="stable")
+    d = lambda a: torch.from_numpy(a).to(cuda_device)
+    for k in sorted({n, max(1, n // 3)}):
+        s_d, tp_d, fp_d = d(scores), d(tp), d(fp)
+        o_tp, o_fp = torch.empty(k, dtype=torch.uint8, device=cuda_device), torch.empty(k, dtype=torch.uint8, device=cuda_device)
+        o_s, o_i = torch.empty(k, dtype=torch.float32, device=cuda_device), torch.empty(k, dtype=torch.int32, device=cuda_device)
+        nb = int(_abi.lib.rod_sort_scores_workspace_bytes(n))
+        ws = torch.empty(nb, dtype=torch.uint8, device=cuda_device)
+        _abi.check(_abi.lib.rod_sort_scores_desc(s_d.data_ptr(), n, k, tp_d.data_ptr(), fp_d.data_ptr(), o_tp.data_ptr(), o_fp.data_ptr(),
+                                                 o_s.data_ptr(), o_i.data_ptr(), ws.data_ptr(), nb,
+                                                 torch.cuda.current_stream(cuda_device).cuda_stream))
+        assert np.array_equal(o_i.cpu().numpy(), order[:k].astype(np.int32))
+        assert np.array_equal(o_tp.cpu().numpy(), tp[order[:k]]) and np.array_equal(o_fp.cpu().numpy(), fp[order[:k]])
+        assert np.array_equal(o_s.cpu().numpy(), scores[order[:k]])
