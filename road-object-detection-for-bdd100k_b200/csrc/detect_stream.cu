@@ -29,6 +29,8 @@
 // nms_kernel), which run only for flagged rows.
 // Prediction depths other than 11 use the plain-load two-pass kernels (hist_kernel, thresh_kernel,
 // collect_kernel: full histogram, exact threshold bin) in front of the same segment kernel.
+#include <cuda_fp16.h>
+
 #include "select_topk.cuh"
 
 namespace rod {
@@ -514,16 +516,36 @@ struct SegParams {
   int chunks, spc, force_dense;
 };
 
-// bytes of the aliased region: sort keys, later {kept boxes, overlap words, batch rows, kept areas}
-// offset of the shrunk candidate boxes inside region A: behind the NMS working set and behind the
-// first k sort keys (still being read while the gather phase writes them)
-__host__ __device__ inline size_t seg_qbox_offset(int k, int keep) {
-  const size_t b = (size_t)keep * (16 + 4) + 64 * 8 * 4, c = (size_t)k * 8;
-  return ((b > c ? b : c) + 15) & ~(size_t)15;
-}
+// Region A of the segment kernel's shared memory: the sort keys first, then (aliased) the NMS working set:
+//   kept rows in packed half form (keep x 16 B), per-warp column masks (64 x 8 x 4 B),
+//   candidates' shrunk boxes in packed half form (k x 8 B), candidates' boxes as packed half rows (k x 16 B)
+__host__ __device__ inline size_t seg_qh_offset(int keep) { return (size_t)keep * 16 + 64 * 8 * 4; }
+__host__ __device__ inline size_t seg_nh_offset(int k, int keep) { return ((seg_qh_offset(keep) + (size_t)k * 8) + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t seg_region_a(int cap, int k, int keep) {
-  const size_t a = (size_t)cap * 16 + 1024 * 4, b = seg_qbox_offset(k, keep) + (size_t)k * 16;
+  const size_t a = (size_t)cap * 16 + 1024 * 4, b = seg_nh_offset(k, keep) + (size_t)k * 16;
   return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+
+// Pair predicate in half precision, two candidates per instruction.  "Row r can intersect candidate box q"
+// is r.ymax > q.ymin && r.ymin < q.ymax && r.xmax > q.xmin && r.xmin < q.xmax.  Rows are stored as
+// (ymax rounded UP, ymin rounded DOWN, xmax UP, xmin DOWN), each duplicated into both halves of a half2;
+// candidates as (ymin DOWN, ymax UP, xmin DOWN, xmax UP), the two candidates of a lane side by side.  Rounding
+// outwards keeps the test a NECESSARY condition of the float predicate (x > y  =>  up(x) > down(y)), so it only
+// filters: every surviving pair still goes through the exact IoU test.  Four HSET2 + two LOP3 test one row
+// against two candidates (eight FSETP before).
+__device__ __forceinline__ unsigned h2u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
+__device__ __forceinline__ __half2 u2h(unsigned u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint4 pack_row(const float4& b) {          // b = (ymin, xmin, ymax, xmax)
+  const __half zu = __float2half_ru(b.z), xd = __float2half_rd(b.x), wu = __float2half_ru(b.w), yd = __float2half_rd(b.y);
+  return make_uint4(h2u(__halves2half2(zu, zu)), h2u(__halves2half2(xd, xd)), h2u(__halves2half2(wu, wu)), h2u(__halves2half2(yd, yd)));
+}
+__device__ __forceinline__ uint2 pack_cand(const float4& q) {         // (ymin DOWN | ymax UP), (xmin DOWN | xmax UP)
+  return make_uint2(h2u(__halves2half2(__float2half_rd(q.x), __float2half_ru(q.z))),
+                    h2u(__halves2half2(__float2half_rd(q.y), __float2half_ru(q.w))));
+}
+// 0xFFFF in the low half: the row can intersect candidate 0, in the high half: candidate 1
+__device__ __forceinline__ unsigned pair_mask(const uint4& row, __half2 qymin, __half2 qymax, __half2 qxmin, __half2 qxmax) {
+  return __hgt2_mask(u2h(row.x), qymin) & __hlt2_mask(u2h(row.y), qymax) & __hgt2_mask(u2h(row.z), qxmin) & __hlt2_mask(u2h(row.w), qxmax);
 }
 
 // exact "fdiv_rn(inter, den) > thr" with a division-free fast path (thr >= 0, den > 0)
@@ -544,10 +566,10 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   const int cap = P.cap, k = P.k, keep = P.keep;
   const size_t regionA = seg_region_a(cap, k, keep);
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_raw);
-  float4* s_kbox = reinterpret_cast<float4*>(s_raw);                                   // [keep] kept boxes
-  unsigned* s_cmw = reinterpret_cast<unsigned*>(s_kbox + keep);                        // [64][kSegWarps] partial column masks
-  float* s_karea = reinterpret_cast<float*>(s_cmw + 64 * kSegWarps);                   // [keep] kept areas
-  float4* s_qbox = reinterpret_cast<float4*>(s_raw + seg_qbox_offset(k, keep));       // [k] shrunk candidate boxes (NMS predicate)
+  uint4* s_kh = reinterpret_cast<uint4*>(s_raw);                                        // [keep] kept rows, packed half form
+  unsigned* s_cmw = reinterpret_cast<unsigned*>(s_kh + keep);                          // [64][kSegWarps] partial column masks
+  uint2* s_qh = reinterpret_cast<uint2*>(s_raw + seg_qh_offset(keep));                 // [k] shrunk candidate boxes, packed half form
+  uint4* s_nh = reinterpret_cast<uint4*>(s_raw + seg_nh_offset(k, keep));              // [k] candidate boxes as packed half rows
   float4* s_box = reinterpret_cast<float4*>(s_raw + regionA);
   float4* s_nbox = s_box + k;
   float* s_area = reinterpret_cast<float*>(s_nbox + k);
@@ -743,7 +765,8 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     // boxes with area <= 0 never overlap anything (TF IOU returns 0): make them unreachable
     const float4 nbv = (area > 0.f) ? nb : make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
     s_nbox[j] = nbv;
-    s_qbox[j] = shrunk(nbv, area);
+    s_qh[j] = pack_cand(shrunk(nbv, area));
+    s_nh[j] = pack_row(nbv);
     s_area[j] = area;
   };
   int gathered = 0;
@@ -786,66 +809,52 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     const int nb = min(bsz, m - p0);
     const int c0 = p0 + lane, c1 = c0 + 32;
     const bool v1 = two && c1 < m;
-    // only the shrunk boxes (computed once in the gather phase) stay in registers; the IoU tests
-    // (rare) re-read box and area
-    const float4 q0 = c0 < m ? s_qbox[c0] : none;
-    const float4 q1 = v1 ? s_qbox[c1] : none;
-    // -- vs the kept list: warp w takes rows w, w+8, ...  First a branch-free pass that only records
-    // which rows intersect the lane's candidates (pipelined broadcast loads + compares), then the
-    // IoU test for the recorded rows only (a few per lane).
+    // the lane's two candidates side by side in half2 registers (shrunk boxes, computed once in the gather phase);
+    // the IoU tests (rare) re-read box and area
+    const uint2 qa = c0 < m ? s_qh[c0] : pack_cand(none);
+    const uint2 qb = v1 ? s_qh[c1] : pack_cand(none);
+    const __half2 qymin = u2h(__byte_perm(qa.x, qb.x, 0x5410)), qymax = u2h(__byte_perm(qa.x, qb.x, 0x7632));
+    const __half2 qxmin = u2h(__byte_perm(qa.y, qb.y, 0x5410)), qxmax = u2h(__byte_perm(qa.y, qb.y, 0x7632));
+    // -- vs the kept list: warp w takes rows w, w+8, ...  First a branch-free pass that only records which rows
+    // can intersect the lane's candidates (pipelined broadcast loads, 16 rows per pass: bit i = candidate 0,
+    // bit 16 + i = candidate 1), then the exact IoU test for the recorded rows only (a few per lane).
     bool d0 = false, d1 = false;
-    for (int jb = warp; jb < nk; jb += 32 * kSegWarps) {
-      unsigned h0 = 0u, h1 = 0u;
-      const int ni = min(32, (nk - jb + kSegWarps - 1) / kSegWarps);      // rows of this pass (warp-uniform)
-      if (two) {
+    for (int jb = warp; jb < nk; jb += 16 * kSegWarps) {
+      unsigned h = 0u;
+      const int ni = min(16, (nk - jb + kSegWarps - 1) / kSegWarps);      // rows of this pass (warp-uniform)
 #pragma unroll 4
-        for (int i = 0; i < ni; ++i) {
-          const float4 kb = s_kbox[jb + i * kSegWarps];
-          h0 |= (unsigned)((kb.z > q0.x) && (q0.z > kb.x) && (kb.w > q0.y) && (q0.w > kb.y)) << i;
-          h1 |= (unsigned)((kb.z > q1.x) && (q1.z > kb.x) && (kb.w > q1.y) && (q1.w > kb.y)) << i;
-        }
-      } else {
-#pragma unroll 4
-        for (int i = 0; i < ni; ++i) {
-          const float4 kb = s_kbox[jb + i * kSegWarps];
-          h0 |= (unsigned)((kb.z > q0.x) && (q0.z > kb.x) && (kb.w > q0.y) && (q0.w > kb.y)) << i;
-        }
-      }
+      for (int i = 0; i < ni; ++i) h |= pair_mask(s_kh[jb + i * kSegWarps], qymin, qymax, qxmin, qxmax) & (0x00010001u << i);
+      unsigned h0 = h & 0xffffu, h1 = h >> 16;
       while (h0 && !d0) {
-        const int j = jb + (__ffs(h0) - 1) * kSegWarps;
+        const int p = s_selected[jb + (__ffs(h0) - 1) * kSegWarps];
         h0 &= h0 - 1;
-        d0 = suppresses(s_kbox[j], s_karea[j], s_nbox[c0], s_area[c0]);
+        d0 = suppresses(s_nbox[p], s_area[p], s_nbox[c0], s_area[c0]);
       }
       while (h1 && !d1) {
-        const int j = jb + (__ffs(h1) - 1) * kSegWarps;
+        const int p = s_selected[jb + (__ffs(h1) - 1) * kSegWarps];
         h1 &= h1 - 1;
-        d1 = suppresses(s_kbox[j], s_karea[j], s_nbox[c1], s_area[c1]);
+        d1 = suppresses(s_nbox[p], s_area[p], s_nbox[c1], s_area[c1]);
       }
     }
     // -- vs the batch itself: warp w takes rows 8w .. 8w+7; bit i of cm = row 8w+i suppresses my column
     unsigned cm0 = 0u, cm1 = 0u;
     {
-      unsigned h0 = 0u, h1 = 0u;
+      unsigned h = 0u;
       const int r0 = warp * (64 / kSegWarps);
 #pragma unroll
-      for (int rr = 0; rr < 64 / kSegWarps; ++rr) {
-        const int rrow = r0 + rr;                       // warp-uniform
-        if (rrow < nb) {
-          const float4 bi = s_nbox[p0 + rrow];
-          // rows >= 32 can only suppress the second candidate; a half batch has no second candidate
-          if (rrow < 32) h0 |= (unsigned)(lane > rrow && (bi.z > q0.x) && (q0.z > bi.x) && (bi.w > q0.y) && (q0.w > bi.y)) << rr;
-          if (two) h1 |= (unsigned)(lane + 32 > rrow && (bi.z > q1.x) && (q1.z > bi.x) && (bi.w > q1.y) && (q1.w > bi.y)) << rr;
-        }
-      }
+      for (int rr = 0; rr < 64 / kSegWarps; ++rr)
+        if (r0 + rr < nb) h |= pair_mask(s_nh[p0 + r0 + rr], qymin, qymax, qxmin, qxmax) & (0x00010001u << rr);
+      // only EARLIER rows of the batch can suppress a candidate (rows >= 32 only the second candidate)
+      unsigned h0 = h & 0xffffu, h1 = h >> 16;
       while (h0) {
         const int rr = __ffs(h0) - 1;
         h0 &= h0 - 1;
-        cm0 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], s_nbox[c0], s_area[c0]) << rr;
+        if (r0 + rr < lane) cm0 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], s_nbox[c0], s_area[c0]) << rr;
       }
       while (h1) {
         const int rr = __ffs(h1) - 1;
         h1 &= h1 - 1;
-        cm1 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], s_nbox[c1], s_area[c1]) << rr;
+        if (r0 + rr < lane + 32) cm1 |= (unsigned)suppresses(s_nbox[p0 + r0 + rr], s_area[p0 + r0 + rr], s_nbox[c1], s_area[c1]) << rr;
       }
     }
     s_cmw[lane * kSegWarps + warp] = cm0;
@@ -892,11 +901,11 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
       // append the survivors to the kept list, in order (lane owns candidates lane and lane + 32)
       if ((K >> lane) & 1ull) {
         const int pos = nk + __popcll(K & ((1ull << lane) - 1ull));
-        s_selected[pos] = c0; s_kbox[pos] = s_nbox[c0]; s_karea[pos] = s_area[c0];
+        s_selected[pos] = c0; s_kh[pos] = s_nh[c0];
       }
       if ((K >> (lane + 32)) & 1ull) {
         const int pos = nk + __popcll(K & ((1ull << (lane + 32)) - 1ull));
-        s_selected[pos] = c1; s_kbox[pos] = s_nbox[c1]; s_karea[pos] = s_area[c1];
+        s_selected[pos] = c1; s_kh[pos] = s_nh[c1];
       }
       if (lane == 0) s_sel = K;
     }
