@@ -126,7 +126,7 @@ hist_kernel(const __grid_constant__ StreamParams P, unsigned* __restrict__ g_his
 // TMA-staged scan (prediction depth C known at compile time)
 // ------------------------------------------------------------------------------------------
 constexpr int kScanBlock = 256;     // threads = anchors per tile
-constexpr int kScanStages = 2;      // TMA tiles in flight per CTA (ring of shared-memory buffers; 3 / 4 measured slower: fewer CTAs per SM)
+constexpr int kScanStages = 2;      // TMA tiles in flight per CTA (ring of shared-memory buffers; 4 measured slower again in round 2: 79 vs 72 us per step)
 constexpr int kListCap = 4096;      // per segment candidate list entries (8 B each)
 constexpr int kMaxChunks = 64;      // CTAs per image; each owns kListCap / chunks list slots per class
 
