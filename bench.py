@@ -73,6 +73,15 @@ def parse_args():
 
 
 # ----------------------------------------------------------------------------------------- helpers
+def measured_traffic(key):
+    """DRAM bytes per launch / step from the committed ncu capture (profiles/r02_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f)[key]["bytes"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -474,7 +483,8 @@ def bench_match(G, table, B, extras):
     res["roofline"] = {
         "bound": "hbm" if alg / (hbm * 1e9) >= pair_flops / (fp32_tops * 1e12) else "fp32_nofma",
         "kernel": "target_fused_kernel", "achieved": alg / t_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": frac_hbm,
-        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "moved_bytes_per_launch": real,
+        "traffic": measured_traffic("target_fused_kernel"), "traffic_note": "ncu DRAM bytes stop at kernel end: the 80 MB of streaming stores are mostly still dirty in L2 (profiles/r02_traffic.json)",
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "moved_bytes_per_launch": real,
         "launch_ms": t1["ms_per_step"], "frac_fp32_nofma": frac_fp32, "fp32_nofma_tops_measured": fp32_tops,
         "pair_flops_per_launch": pair_flops,
         "note": "1 launch = 1 step; algorithmic = SURVEY 8d M (124N+20G B/img), moved = 84N+20G; FP32 no-FMA pair bound (14NG flops) beside it"}
@@ -620,7 +630,8 @@ def bench_detect(G, table, B, kind, extras, primary):
            "kernels_per_step": ["sample_kernel", "scan_kernel", "segment_kernel", "topk_segment_kernel / nms_kernel (flagged segments only)"],
            "detections_per_image": float(stage[0, 1:].sum().item()) / B,
            "roofline": {"bound": "hbm", "kernel": "whole step (sample + scan + segment kernels)", "achieved": alg / t_s / 1e9,
-                        "peak": hbm, "unit": "GB/s", "frac": alg / t_s / 1e9 / hbm, "traffic": None, "peak_source": peak_src,
+                        "peak": hbm, "unit": "GB/s", "frac": alg / t_s / 1e9 / hbm, "traffic": measured_traffic("decode_nms_step") if kind == "normal" else None,
+                        "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg, "launch_ms": t1["ms_per_step"]},
            "config": {"workload": workload_name("nms_stress" if kind == "stress" else "decode_nms") + ("" if kind in ("normal", "stress") else " [%s-clustered scores]" % kind),
                       "batch_per_gpu": B, "global_batch": B * G.world, "image": "512x512", "anchors": N,
