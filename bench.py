@@ -701,6 +701,68 @@ def e2e_detect(G, table, B, host, kw):
             "api": "net_tools.decode_detected_bboxes on pinned host inputs (1 H2D copy); scores + boxes read back; 2 batches in flight"}
 
 
+def bench_next_rows(G, table, B_m, B_d):
+    """SURVEY section 8 'next' rows, two scalars each (N = 1 only): f-1 decode_nms fed with class logits (softmax fused
+    into the scan pass), f-3 targets + refine_loss + det_clf_loss forward as a graph replay and forward + backward eagerly."""
+    torch = G.torch
+    from rodet_b200 import synth
+    from rodet_b200.utils import net_tools
+    dev, N, out = G.dev, table.n, {}
+    lay = lambda flat_, tail: [torch.from_numpy(a).to(dev) for a in split_np(flat_, SHAPES, tail)]
+    # f-1
+    sets = []
+    for s in range(3):
+        first = 700_000 + s * B_d
+        z = np.stack([synth.class_logits(first + b, N_ANCHORS) for b in range(B_d)])
+        _, ro, do = host_inputs_detect(synth, first, 1, "normal")
+        ro = np.stack([synth.head_offsets(first + b, N_ANCHORS, 0, 0.1, 0.2) for b in range(B_d)])
+        do = np.stack([synth.head_offsets(first + b, N_ANCHORS, 1, 0.1, 0.2) for b in range(B_d)])
+        sets.append({"z": lay(z, (N_CLASSES,)), "ro": lay(ro, (4,)), "do": lay(do, (4,)), "ws": net_tools.detect_workspace(table, B_d, TOP_K, dev)})
+    kw = dict(select_threshold=SELECT_THR, nms_threshold=NMS_THR, top_k=TOP_K, keep_top_k=KEEP, from_logits=True)
+
+    def step_logits(i):
+        s = sets[i % 3]
+        s["out"] = net_tools.decode_detected_bboxes(table, s["ro"], s["do"], s["z"], workspace=s["ws"], **kw)
+    K = 24
+    g = G.capture(step_logits, K)
+    t = G.time_loops(g.replay if g is not None else (lambda: [step_logits(i) for i in range(K)]), K)
+    out["decode_nms_logits_ms_per_step"] = t["ms_per_step"]
+    out["decode_nms_logits_value"] = B_d / (t["ms_per_step"] * 1e-3)
+    del sets
+    # f-3
+    c, l, k, ro = host_inputs_match(synth, 800_000, B_m)
+    cen, lab, cnt = torch.from_numpy(c).to(dev), torch.from_numpy(l).to(dev), torch.from_numpy(k).to(dev)
+    ro_l = lay(ro, (4,))
+    do_l = lay(np.stack([synth.head_offsets(800_000 + b, N_ANCHORS, 1) for b in range(B_m)]), (4,))
+    clf_l = lay(np.stack([synth.class_logits(800_000 + b, N_ANCHORS) for b in range(B_m)]), (N_CLASSES,))
+    buf = net_tools.target_buffers(table, B_m, dev)
+
+    def forward(ro_, do_, clf_):
+        arm, det = net_tools.target_gen(table, cen, lab, [t_.detach() for t_ in ro_], gt_counts=cnt, out=buf)
+        rl = net_tools.refine_loss(ro_, arm[0], arm[3])
+        dl, cl = net_tools.det_clf_loss(ro_, clf_, do_, det[0], det[1], det[2], det[3])
+        return rl + dl + cl
+    keep = {}
+
+    def step_fwd(i):
+        with torch.no_grad():
+            keep["loss"] = forward(ro_l, do_l, clf_l)
+    K = 8
+    g = G.capture(step_fwd, K)
+    t = G.time_loops(g.replay if g is not None else (lambda: [step_fwd(i) for i in range(K)]), K)
+    out["targets_losses_forward_graph_ms"] = t["ms_per_step"]
+    leaves = [[x.clone().requires_grad_(True) for x in ts] for ts in (ro_l, do_l, clf_l)]
+
+    def step_bwd():
+        for ts in leaves:
+            for x in ts:
+                x.grad = None
+        forward(*leaves).backward()
+    t = G.time_loops(step_bwd, 1, min_ms=30.0, warm_loops=3, max_loops=40)
+    out["targets_losses_forward_backward_eager_ms"] = t["ms_per_step"]
+    return out
+
+
 def flat(line, prefix, r, keys=("value", "ms_per_step", "value_overlapped", "ms_per_step_overlapped", "over_rate")):
     for k in keys:
         if k in r:
@@ -709,9 +771,7 @@ def flat(line, prefix, r, keys=("value", "ms_per_step", "value_overlapped", "ms_
         line["%s_roofline_frac" % prefix] = r["roofline"]["frac"]
     if "e2e" in r:
         line["%s_e2e_value" % prefix] = r["e2e"]["value"]
-    if "timing" in r:
-        line["%s_timed_ms" % prefix] = r["timing"]["timed_ms"]
-    if "config" in r:
+    if "config" in r and prefix == "decode_nms":
         line["%s_batch_per_gpu" % prefix] = r["config"]["batch_per_gpu"]
 
 
@@ -779,6 +839,8 @@ def main():
         flat(line, "nms_stress", bench_detect(G, table, B_d, "stress", False, False))
         flat(line, "decode_nms_clustered", bench_detect(G, table, B_d, "quadrant", False, False))
         flat(line, "decode_nms_bumps", bench_detect(G, table, B_d, "bumps", False, False))
+        if G.world == 1:
+            line.update(bench_next_rows(G, table, B_m, B_d))
 
     if G.rank == 0 and not args.skip_cpu and G.world == 1:
         cb = cpu_baselines(args, B_m, B_d)
