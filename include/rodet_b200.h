@@ -149,6 +149,13 @@ int rod_target_fused(const rod_layout_t* layout, const float* anchors_corner,
 int rod_decode(const rod_layout_t* layout, const float* anchors_center,
                const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
                int to_corner, float* out, void* stream);
+/* Opt-in extra WITHOUT a reference counterpart (the reference decodes refine_out + det_out once,
+ * SURVEY.md 0.5): the RefineDet cascade named by BASELINE.json's north star — det_out decoded against
+ * the refined anchors decode(anchors, refine_out), i.e. decode_locations_one_layer applied twice with its
+ * corner -> re-derived-centre anchor step (utils/net_tools.py:156-171) in between.  Never the default. */
+int rod_decode_cascade(const rod_layout_t* layout, const float* anchors_center,
+                       const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
+                       int to_corner, float* out, void* stream);
 
 /* ---- a6  encode one box against every anchor -------------------------------------
  * Replaces encode_locations_one_layer (utils/net_tools.py:147-179): center_bbox is a

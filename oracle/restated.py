@@ -282,6 +282,13 @@ def decode_corner(table, refine_out, det_out):
     return center_to_corner(decode(table.center, s))
 
 
+def decode_cascade_corner(table, refine_out, det_out):
+    """Opt-in extra without a reference counterpart: det_out decoded against the refined anchors, i.e.
+    decode_locations_one_layer applied twice (anchors -> corners -> re-derived centre form in between, :156-171)."""
+    refined = corner_to_center(center_to_corner(decode(table.center, refine_out)))
+    return center_to_corner(decode(refined, det_out))
+
+
 # --------------------------------------------------------------------------- #
 # a11  select  (utils/net_tools.py:658-736)
 # --------------------------------------------------------------------------- #

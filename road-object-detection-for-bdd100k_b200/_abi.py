@@ -46,6 +46,7 @@ SIGNATURES = {
     "rod_target_fused": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _YP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_dl_target_fused": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_decode": (_i, [_LP, _vp, _YP, _YP, _i, _i, _vp, _vp]),
+    "rod_decode_cascade": (_i, [_LP, _vp, _YP, _YP, _i, _i, _vp, _vp]),
     "rod_encode_one_box": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "rod_center_to_corner": (_i, [_vp, _vp, _i64, _vp]),
     "rod_corner_to_center": (_i, [_vp, _vp, _i64, _vp]),

@@ -65,6 +65,10 @@ odm_target_kernel(const __grid_constant__ Layout L, const __grid_constant__ Thre
   __stcs(iou + o, j);
 }
 
+// has_det: 0 single decode of refine_out; 1 the reference's call site decode(anchors, refine_out + det_out)
+// (evaluate.py:141); 2 (opt-in extra, no reference counterpart) the RefineDet cascade: the refined anchors
+// decode(anchors, refine_out) are treated as a new anchor layer and det_out is decoded against them, i.e.
+// decode_locations_one_layer applied twice with its own corner -> re-derived centre step in between (:156-171).
 __global__ void __launch_bounds__(kEwBlock)
 decode_kernel(const __grid_constant__ Layout L, const float* __restrict__ center,
               const __grid_constant__ LayeredF refine_out, const __grid_constant__ LayeredF det_out,
@@ -74,11 +78,18 @@ decode_kernel(const __grid_constant__ Layout L, const float* __restrict__ center
   if (n >= L.n_total) return;
   const int l = layer_of(L, n);
   float4 o = ldg4(lp4(refine_out, L, l, b, n));
-  if (has_det) {                         // evaluate.py:141 (refine_out + det_out)
+  float4 r;
+  if (has_det == 2) {
     const float4 d = ldg4(lp4(det_out, L, l, b, n));
-    o = make_float4(__fadd_rn(o.x, d.x), __fadd_rn(o.y, d.y), __fadd_rn(o.z, d.z), __fadd_rn(o.w, d.w));
+    const float4 refined = corner_to_center(center_to_corner(decode_center(ldg4(center + 4ll * n), o)));
+    r = decode_center(refined, d);
+  } else {
+    if (has_det) {                       // evaluate.py:141 (refine_out + det_out)
+      const float4 d = ldg4(lp4(det_out, L, l, b, n));
+      o = make_float4(__fadd_rn(o.x, d.x), __fadd_rn(o.y, d.y), __fadd_rn(o.z, d.z), __fadd_rn(o.w, d.w));
+    }
+    r = decode_center(ldg4(center + 4ll * n), o);
   }
-  float4 r = decode_center(ldg4(center + 4ll * n), o);
   if (to_corner) r = center_to_corner(r);   // evaluate.py:142
   st4_cs(out + 4 * ((long long)b * L.n_total + n), r);
 }
@@ -124,9 +135,27 @@ extern "C" int rod_odm_target(const rod_layout_t* layout, const float* anchors_c
   return ROD_OK;
 }
 
+static int decode_impl(const rod_layout_t* layout, const float* anchors_center, const rod_layered_t* refine_out,
+                       const rod_layered_t* det_out, int batch, int to_corner, float* out, void* stream, int cascade);
+
 extern "C" int rod_decode(const rod_layout_t* layout, const float* anchors_center,
                           const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
                           int to_corner, float* out, void* stream) {
+  return decode_impl(layout, anchors_center, refine_out, det_out, batch, to_corner, out, stream, 0);
+}
+
+extern "C" int rod_decode_cascade(const rod_layout_t* layout, const float* anchors_center,
+                                  const rod_layered_t* refine_out, const rod_layered_t* det_out, int batch,
+                                  int to_corner, float* out, void* stream) {
+  if (det_out == nullptr) {
+    rod::set_error("rod_decode_cascade: det_out is NULL");
+    return ROD_E_INVALID;
+  }
+  return decode_impl(layout, anchors_center, refine_out, det_out, batch, to_corner, out, stream, 1);
+}
+
+static int decode_impl(const rod_layout_t* layout, const float* anchors_center, const rod_layered_t* refine_out,
+                       const rod_layered_t* det_out, int batch, int to_corner, float* out, void* stream, int cascade) {
   using namespace rod;
   int rc = check_layout(layout);
   if (rc) return rc;
@@ -141,7 +170,7 @@ extern "C" int rod_decode(const rod_layout_t* layout, const float* anchors_cente
   const LayeredF ro = to_layered_f(refine_out, nl);
   decode_kernel<<<grid, kEwBlock, 0, (cudaStream_t)stream>>>(L, anchors_center, ro,
                                                               det_out ? to_layered_f(det_out, nl) : ro,
-                                                              det_out ? 1 : 0, to_corner, out);
+                                                              det_out ? (cascade ? 2 : 1) : 0, to_corner, out);
   ROD_LAUNCH_CHECK("decode_kernel");
   return ROD_OK;
 }

@@ -27,7 +27,7 @@ __all__ = [
     "init_anchor", "n_anchor_each_layer", "anchors_one_layer", "anchors_all_layer",
     "encode_locations_one_layer", "decode_locations_one_layer", "jaccard", "refine_groundtruth",
     "det_groundtruth", "target_gen", "target_buffers", "bboxes_select_one_layer", "bboxes_select_all_layers", "detected_bboxes",
-    "decode_detected_bboxes", "detect_workspace", "detect_fallback_flags", "softmax",
+    "decode_detected_bboxes", "decode_locations_cascade", "detect_workspace", "detect_fallback_flags", "softmax",
 ]
 
 
@@ -153,6 +153,30 @@ def _decode(table, refine_out, det_out, to_corner):
                                           a.many(det_out), 1 if to_corner else 0, a.one(out),
                                           _abi.stream_ptr(dev)))
     return out
+
+
+def decode_locations_cascade(anchors_all_layer, refine_out, det_out, to_corner=True):
+    """Opt-in extra with NO reference counterpart (the reference decodes `refine_out + det_out` once, evaluate.py:141):
+    the RefineDet cascade of BASELINE.json's north star — `det_out` decoded against the refined anchors
+    `decode(anchors, refine_out)`, i.e. decode_locations_one_layer applied twice with its own corner -> re-derived-centre
+    anchor step in between.  Returns the per-layer list of [B,fh,fw,A,4] boxes (corner form by default), ready for
+    `detected_bboxes(predictions, localisations)`.  Results differ from the reference's; never used by default."""
+    ro = [_f32(t, "refine_out") for t in refine_out]
+    do = [_f32(t, "det_out") for t in det_out]
+    dev = ro[0].device
+    table = table_for(anchors_all_layer, dev)
+    _check_list(ro, table, "refine_out")
+    _check_list(do, table, "det_out")
+    B = ro[0].shape[0]
+    out = torch.empty((B, table.n, 4), dtype=torch.float32, device=dev)
+    if B:
+        a, bb = _abi.DLArgs(), [-1]
+        with _abi.device_guard(dev):
+            r = _abi.layered_arg(ro, table, 4, torch.float32, a, bb)
+            d = _abi.layered_arg(do, table, 4, torch.float32, a, bb)
+            _abi.check(_abi.lib.rod_decode_cascade(table.layout, table.center.data_ptr(), r, d, B, 1 if to_corner else 0,
+                                                   out.data_ptr(), _abi.stream_ptr(dev)))
+    return _abi.LayerList(out, table, True, False)
 
 
 def jaccard(anchors, corner_bbox):

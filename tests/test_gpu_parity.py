@@ -259,3 +259,27 @@ def test_eval_matching_vs_reference_fixture(rb):
     o = R.bboxes_matching_batch(2, d_s, d_b, g_l, g_b, g_d)
     assert np.array_equal(n2.cpu().numpy(), o[0]) and np.array_equal(tp2.cpu().numpy(), o[1])
     assert np.array_equal(fp2.cpu().numpy(), o[2]) and o[1].sum() > 20
+
+
+def test_cascade_decode_extra(cuda_device):
+    """Opt-in RefineDet cascade decode (no reference counterpart; BASELINE north star): bit-exact against the restated
+    composition of two reference decodes, different from the reference's sum-then-decode, and usable as the
+    `localisations` of detected_bboxes."""
+    from rodet_b200 import synth
+    from rodet_b200.utils import net_tools
+    anchors = golden_anchors("418")
+    table = R.AnchorTable(anchors)
+    B = 2
+    ro = np.stack([synth.head_offsets(b, table.n, 0) for b in range(B)])
+    do = np.stack([synth.head_offsets(b, table.n, 1) for b in range(B)])
+    ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), cuda_device), to_cuda_list(do, table.shapes, (4,), cuda_device)
+    out = net_tools.decode_locations_cascade(anchors, ro_l, do_l)
+    got = flat_from_list(out, 1)
+    assert bit_equal(got, R.decode_cascade_corner(table, ro, do))
+    assert not np.allclose(got, R.decode_corner(table, ro, do))            # not the reference's single decode
+    probs = np.stack([synth.class_probs(b, table.n) for b in range(B)])
+    rs, rb = net_tools.detected_bboxes(to_cuda_list(probs, table.shapes, (11,), cuda_device), out, select_threshold=0.3,
+                                       nms_threshold=0.45, top_k=400, keep_top_k=200)
+    o_s, o_b = R.detected_bboxes(probs, got, 0.3, 0.45, None, 400, 200)
+    for c in range(1, 11):
+        assert bit_equal(rs[c].cpu().numpy(), o_s[c]) and bit_equal(rb[c].cpu().numpy(), o_b[c])
