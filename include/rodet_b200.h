@@ -107,6 +107,19 @@ int rod_arm_match_encode(const rod_layout_t* layout, const float* anchors_corner
                          float* gt, float* cbboxes, int32_t* out_labels, int32_t* pos_mask,
                          int32_t* match_idx, void* stream);
 
+/* Opt-in extra WITHOUT a reference counterpart, the "forced match" named by BASELINE.json's
+ * north star: a post-pass over rod_arm_match_encode's outputs in which every GT box also claims the anchor
+ * it overlaps best (argmax over the anchor axis, lowest anchor index on ties, IoU > 0) whatever the layer
+ * threshold; several GT boxes on one anchor: highest IoU wins, ties lowest GT index.  The reference's
+ * JACCARD_BIGGER has no such step (utils/net_tools.py:405-408); never the default.
+ * workspace: rod_arm_forced_match_workspace_bytes(batch, gmax) bytes, 8-byte aligned. */
+size_t rod_arm_forced_match_workspace_bytes(int batch, int gmax);
+int rod_arm_forced_match(const rod_layout_t* layout, const float* anchors_corner,
+                         const float* anchors_center, const float* center_bboxes, const void* labels,
+                         int labels_i64, const int32_t* gt_counts, int batch, int gmax, float* gt,
+                         float* cbboxes, int32_t* out_labels, int32_t* pos_mask, int32_t* match_idx,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a10  ODM target generation --------------------------------------------------
  * Replaces det_groundtruth (utils/net_tools.py:431-475).
  * thresholds: host float[n_layers] = config.det_pos_jac_val_all_layers.

@@ -252,6 +252,30 @@ def arm_match_encode(table, center_bboxes, labels, thresholds=REFINE_POS_JAC,
     return gt, cbo, labo, pos.astype(np.int32), idx
 
 
+def forced_match(table, center_bboxes, labels, arm_out):
+    """Opt-in extra without a reference counterpart: on top of arm_match_encode's outputs (one image) every GT box claims
+    the anchor it overlaps best (argmax over anchors, first = lowest index, IoU > 0); several GT boxes on one anchor:
+    highest IoU wins, ties lowest GT index.  Returns new (gt, cbboxes, labels, pos, idx)."""
+    cb = np.asarray(center_bboxes, dtype=f32).reshape(-1, 4)
+    lab = np.asarray(labels).astype(np.int32)
+    gt, cbo, labo, pos, idx = [np.array(a, copy=True) for a in arm_out]
+    jac = jaccard(table.corner[None, :, :], center_to_corner(cb)[:, None, :])     # [G,N]
+    jac = np.where(np.isnan(jac), f32(0), jac)
+    best_n, best_v = jac.argmax(axis=1), jac.max(axis=1)
+    for g in range(cb.shape[0]):
+        if not best_v[g] > 0:
+            continue
+        rivals = [o for o in range(cb.shape[0]) if o != g and best_v[o] > 0 and best_n[o] == best_n[g] and
+                  (best_v[o] > best_v[g] or (best_v[o] == best_v[g] and o < g))]
+        if rivals:
+            continue
+        n = int(best_n[g])
+        gt[n] = encode(table.center[n], cb[g]) + f32(0)
+        cbo[n] = cb[g] + f32(0)
+        labo[n], pos[n], idx[n] = lab[g], 1, g
+    return gt, cbo, labo, pos, idx
+
+
 # --------------------------------------------------------------------------- #
 # a10  ODM target generation  (utils/net_tools.py:431-475)
 # --------------------------------------------------------------------------- #

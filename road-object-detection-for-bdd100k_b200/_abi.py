@@ -41,6 +41,8 @@ SIGNATURES = {
     "rod_anchor_table": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "rod_anchor_table_from_grid": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rod_arm_match_encode": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rod_arm_forced_match_workspace_bytes": (_sz, [_i, _i]),
+    "rod_arm_forced_match": (_i, [_LP, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_odm_target": (_i, [_LP, _vp, _vp, _YP, _YP, _YP, _YP, _YP, _i, _vp, _vp, _vp, _vp, _vp]),
     "rod_target_fused_workspace_bytes": (_sz, []),
     "rod_target_fused": (_i, [_LP, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _YP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -197,13 +197,15 @@ def jaccard(anchors, corner_bbox):
 
 # --------------------------------------------------------------------------------- a9 ARM
 def refine_groundtruth(anchors_all_layer, center_bboxes, labels, method, scope="refine_encode",
-                       gt_counts=None, return_match_index=False, thresholds=None):
+                       gt_counts=None, return_match_index=False, thresholds=None, forced_match=False):
     """ARM matching + encoding (utils/net_tools.py:270-428).
 
     Per image (reference form): center_bboxes[G,4], labels[G] -> four lists over layers of
     gt[fh,fw,A,4], cbboxes[fh,fw,A,4], labels[fh,fw,A,1] (int32), pos_mask[fh,fw,A,1] (int32).
     Batched extension: center_bboxes[B,Gmax,4], labels[B,Gmax], gt_counts[B] (int32, >= 1) ->
-    the same lists with a leading batch dimension."""
+    the same lists with a leading batch dimension.
+    forced_match=True (opt-in extra, NO reference counterpart, JACCARD_BIGGER only): every GT box additionally claims
+    the anchor it overlaps best, whatever the layer threshold (SSD / RefineDet bipartite step; rod_arm_forced_match)."""
     if method == config.refine_method.JACCARD_TOPK:
         raise ValueError('Not support now')                       # :424
     if method not in (config.refine_method.NEAREST_NEIGHBOR, config.refine_method.JACCARD_BIGGER):
@@ -241,6 +243,16 @@ def refine_groundtruth(anchors_all_layer, center_bboxes, labels, method, scope="
             table.layout, a.one(table.corner), a.one(table.center), thr, a.one(cb), a.one(lab),
             a.one(gt_counts), int(method.value), a.one(gt), a.one(cbo), a.one(lbo), a.one(pos), a.one(idx),
             _abi.stream_ptr(dev)))
+        if forced_match:
+            if method != config.refine_method.JACCARD_BIGGER:
+                raise ValueError("forced_match extends the JACCARD_BIGGER branch only")
+            nb = int(_abi.lib.rod_arm_forced_match_workspace_bytes(B, cb.shape[1]))
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _abi.check(_abi.lib.rod_arm_forced_match(
+                table.layout, table.corner.data_ptr(), table.center.data_ptr(), cb.data_ptr(), lab.data_ptr(),
+                1 if lab.dtype == torch.int64 else 0, gt_counts.data_ptr() if gt_counts is not None else None, B, cb.shape[1],
+                gt.data_ptr(), cbo.data_ptr(), lbo.data_ptr(), pos.data_ptr(), idx.data_ptr() if idx is not None else None,
+                ws.data_ptr(), nb, _abi.stream_ptr(dev)))
     LL = _abi.LayerList
     res = (LL(gt, table, batched, False), LL(cbo, table, batched, False), LL(lbo, table, batched, True),
            LL(pos, table, batched, True))

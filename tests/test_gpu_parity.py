@@ -283,3 +283,43 @@ def test_cascade_decode_extra(cuda_device):
     o_s, o_b = R.detected_bboxes(probs, got, 0.3, 0.45, None, 400, 200)
     for c in range(1, 11):
         assert bit_equal(rs[c].cpu().numpy(), o_s[c]) and bit_equal(rb[c].cpu().numpy(), o_b[c])
+
+
+@pytest.mark.parametrize("layout,first,B", [("418", 60, 3), ("512", 64, 2)])
+def test_forced_match_extra(cuda_device, layout, first, B):
+    """Opt-in forced match (no reference counterpart; BASELINE north star): every GT box claims its best anchor.  Against
+    the restated definition, bit-exact; the default call is unchanged; a GT no anchor reaches the threshold for gains a
+    positive."""
+    from rodet_b200 import config, synth
+    from rodet_b200.utils import net_tools
+    anchors = golden_anchors(layout)
+    table = R.AnchorTable(anchors)
+    corner, labels, counts = synth.gt_batch(first, B, max_gt=30)
+    corner[0, 0] = np.array([0.40, 0.40, 0.404, 0.401], np.float32)      # a sliver no anchor matches by threshold
+    center = R.corner_to_center(corner).astype(np.float32)
+    for b in range(B):
+        center[b, counts[b]:] = 0
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    JB = config.refine_method.JACCARD_BIGGER
+    base = net_tools.refine_groundtruth(anchors, d(center), d(labels), JB, gt_counts=d(counts), return_match_index=True)
+    forced = net_tools.refine_groundtruth(anchors, d(center), d(labels), JB, gt_counts=d(counts), return_match_index=True,
+                                          forced_match=True)
+    fl = lambda ts, k: [flat_from_list(x, t) for x, t in zip(ts, k)]
+    gb, gf = fl(base, (1, 1, 1, 1, 0)), fl(forced, (1, 1, 1, 1, 0))
+    gained = 0
+    for b in range(B):
+        k = int(counts[b])
+        o = R.arm_match_encode(table, center[b, :k], labels[b, :k])
+        assert np.array_equal(gb[3][b, :, 0], o[3]) and np.array_equal(gb[4][b], o[4])          # default path unchanged
+        f = R.forced_match(table, center[b, :k], labels[b, :k], o)
+        assert np.array_equal(gf[3][b, :, 0], f[3]) and np.array_equal(gf[4][b], f[4]) and np.array_equal(gf[2][b, :, 0], f[2])
+        assert bit_equal(gf[1][b], f[1]) and bit_equal(gf[0][b], f[0])
+        gained += int(f[3].sum() - o[3].sum())
+        claimed = set(int(v) for v in f[4][f[3] > 0])
+        best = R.jaccard(table.corner[None], R.center_to_corner(center[b, :k])[:, None]).argmax(1)
+        for g in range(k):            # a GT without any positive lost its best anchor to a rival GT that claims the same anchor
+            assert g in claimed or any(o2 != g and best[o2] == best[g] for o2 in range(k))
+    assert gained > 0
+    with pytest.raises(ValueError):
+        net_tools.refine_groundtruth(anchors, d(center), d(labels), config.refine_method.NEAREST_NEIGHBOR, gt_counts=d(counts),
+                                     forced_match=True)
