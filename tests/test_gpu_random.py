@@ -460,3 +460,24 @@ def test_target_gen_fused_bit_exact(env, layout, B, first):
     arm3, det3 = env.nt.target_gen(env.anchors[layout], t(center), t(labels), ro_l, gt_counts=t(counts), need_cbboxes=False)
     assert arm3[1] is None and arm3[2] is None and torch.equal(arm3[0].flat, arm[0].flat)
     assert torch.equal(det3[0].flat.view(torch.int32), det[0].flat.view(torch.int32)) and torch.equal(det3[1].flat, det[1].flat)
+
+
+def test_detect_tier2_rescues_a_too_high_cut(env):
+    """The sample overestimates how many candidates lie above cut_hi (the sampled anchors carry the high scores), so tier 1
+    ends up with fewer than top_k entries; the candidates between cut_lo and cut_hi (tier 2) complete the segment WITHOUT the
+    general kernels, bit-exactly."""
+    layout, B = "512", 2
+    table = env.otable[layout]
+    probs, ro, do = _detect_inputs(env, layout, 900, B, stress=False)
+    sampled = np.flatnonzero((np.arange(table.n) % 19) == 9)
+    others = np.flatnonzero((np.arange(table.n) % 19) != 9)
+    rng = np.random.default_rng(17)
+    for b in range(B):
+        col = np.full(table.n, 0.01, np.float32)
+        hi = rng.choice(sampled, 100, replace=False)
+        col[hi] = rng.uniform(0.6, 1.0, 100).astype(np.float32)            # 34th best sample ~0.86 = cut_hi, 84th ~0.66 = cut_lo
+        band = rng.choice(others, 600, replace=False)
+        col[band] = rng.uniform(0.70, 0.80, 600).astype(np.float32)        # invisible to the sample, between the two cuts
+        probs[b, :, 3] = col
+    ndet, flags = _detect_vs_c_oracle(env, layout, probs, ro, do)
+    assert ndet > 0 and flags[3].sum() == 0, "class 3 must be completed from tier 2, not by the general kernels"
