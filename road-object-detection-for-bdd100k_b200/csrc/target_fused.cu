@@ -23,6 +23,19 @@ namespace rod {
 
 constexpr int kTfBlock = 128;
 
+// ld.shared with a 32-bit shared-window address computed once per CTA: through a generic pointer the compiler
+// re-derives the window base (S2UR SR_CgaCtaId + 3 uniform ops) in every iteration of the GT walk
+__device__ __forceinline__ float4 lds4(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds1(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 struct FusedParams {
   Layout L;
   Thresholds Ta, To;                    // ARM / ODM per-layer IoU thresholds (config.py:79-80)
@@ -45,21 +58,30 @@ __global__ void __launch_bounds__(kTfBlock, 10)
 target_fused_kernel(const __grid_constant__ FusedParams P) {
   extern __shared__ float4 s_box[];                         // [gmax] GT corners (net_tools.py:323)
   float* s_area = reinterpret_cast<float*>(s_box + P.gmax);  // [gmax] GT areas (:265)
+  unsigned a_box, a_area;                                   // (opaque moves: ptxas otherwise rematerialises the window base per use)
+  asm volatile("mov.u32 %0, %1;" : "=r"(a_box) : "r"((unsigned)__cvta_generic_to_shared(s_box)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(a_area) : "r"((unsigned)__cvta_generic_to_shared(s_area)));
 
-  __shared__ unsigned s_item;
+  __shared__ int s_tile, s_img;                             // the current work item, decoded by thread 0 (tile < 0: none left)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = P.L.n_total;
   const float4 none = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);   // intersects nothing
   const unsigned total = (unsigned)P.tiles * (unsigned)P.batch;
 
-  if (tid == 0) s_item = atomicAdd(P.sched, 1u);
+  // item -> (tile, image): all images' last tile first, then the one before, ... (descending cost); one division per
+  // item per CTA (thread 0), not per thread
+  auto fetch = [&]() {
+    const unsigned item = atomicAdd(P.sched, 1u);
+    const bool any = item < total;
+    s_tile = any ? P.tiles - 1 - (int)(item / (unsigned)P.batch) : -1;
+    s_img = any ? (int)(item % (unsigned)P.batch) : 0;
+  };
+  if (tid == 0) fetch();
   __syncthreads();
-  unsigned item = s_item;
-  while (item < total) {
-    // item -> (tile, image): all images' last tile first, then the one before, ... (descending cost)
-    const int t = P.tiles - 1 - (int)(item / (unsigned)P.batch), b = (int)(item % (unsigned)P.batch);
-    __syncthreads();                                        // every warp has read s_item and is done with the GT list
-    if (tid == 0) s_item = atomicAdd(P.sched, 1u);          // next item: the fetch overlaps this tile
+  int t = s_tile, b = s_img;
+  while (t >= 0) {
+    __syncthreads();                                        // every warp has read the item and is done with the GT list
+    if (tid == 0) fetch();                                  // next item: the fetch overlaps the GT staging
     int count = P.counts ? P.counts[b] : P.gmax;
     count = min(max(count, 0), P.gmax);
     const float* gt_img = P.gtb + 4ll * b * P.gmax;
@@ -70,7 +92,7 @@ target_fused_kernel(const __grid_constant__ FusedParams P) {
       s_area[g] = __fmul_rn(__fsub_rn(gc.z, gc.x), __fsub_rn(gc.w, gc.y));
     }
     __syncthreads();
-    item = s_item;
+    const int t_next = s_tile, b_next = s_img;
     {
     const int n = t * kTfBlock + warp * 32 + lane;
     const bool valid = n < N;
@@ -90,20 +112,20 @@ target_fused_kernel(const __grid_constant__ FusedParams P) {
       const int g = base + lane;
       bool hit = false;
       if (g < count) {
-        const float4 gc = s_box[g];
+        const float4 gc = lds4(a_box + 16u * (unsigned)g);
         hit = (gc.z > t_ymin) && (gc.x < t_ymax) && (gc.w > t_xmin) && (gc.y < t_xmax);
       }
       unsigned m = __ballot_sync(0xffffffffu, hit);
       while (m) {                                           // ascending GT index
         const int j = base + __ffs(m) - 1;
         m &= m - 1;
-        const float4 gc = s_box[j];                         // broadcast
+        const float4 gc = lds4(a_box + 16u * (unsigned)j);  // broadcast
         // positive intersection <=> both extents > 0 (x - y > 0 <=> x > y in IEEE arithmetic without FTZ)
         const float h = __fsub_rn(fminf(a.z, gc.z), fmaxf(a.x, gc.x));
         const float w = __fsub_rn(fminf(a.w, gc.w), fmaxf(a.y, gc.y));
         if (h > 0.f && w > 0.f) {
           const float inter = __fmul_rn(h, w);
-          const float uni = __fadd_rn(__fsub_rn(vol_a, inter), s_area[j]);
+          const float uni = __fadd_rn(__fsub_rn(vol_a, inter), lds1(a_area + 4u * (unsigned)j));
           const float jac = __fdiv_rn(inter, uni);
           if (jac > best) { best = jac; bi = j; }
         }
@@ -155,6 +177,7 @@ target_fused_kernel(const __grid_constant__ FusedParams P) {
     __stcs(P.iou + o, j);
     }   // valid
     }   // tile
+    t = t_next; b = b_next;
   }
   // leave: the last CTA resets the counters for the next launch
   if (tid == 0) {
