@@ -32,6 +32,11 @@ arm_jaccard_bigger_kernel(const __grid_constant__ Layout L, const __grid_constan
                           int32_t* __restrict__ out_idx) {
   extern __shared__ float4 s_box[];                       // [gmax] GT corners (net_tools.py:323)
   float* s_area = reinterpret_cast<float*>(s_box + gmax);  // [gmax] (g_ymax-g_ymin)*(g_xmax-g_xmin), :265
+  // 32-bit shared-window addresses in opaque registers: through generic pointers ptxas re-derives the window base
+  // (S2UR SR_CgaCtaId + 3 uniform ops) in every iteration of the GT walk (see target_fused.cu)
+  unsigned a_box, a_area;
+  asm volatile("mov.u32 %0, %1;" : "=r"(a_box) : "r"((unsigned)__cvta_generic_to_shared(s_box)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(a_area) : "r"((unsigned)__cvta_generic_to_shared(s_area)));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -78,14 +83,14 @@ arm_jaccard_bigger_kernel(const __grid_constant__ Layout L, const __grid_constan
     const int g = base + lane;
     bool hit = false;
     if (g < count) {
-      const float4 gc = s_box[g];
+      const float4 gc = lds_f4(a_box + 16u * (unsigned)g);
       hit = (gc.z > t_ymin) && (gc.x < t_ymax) && (gc.w > t_xmin) && (gc.y < t_xmax);
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
     while (m) {                                        // ascending GT index
       const int j = base + __ffs(m) - 1;
       m &= m - 1;
-      const float4 gc = s_box[j];                      // broadcast
+      const float4 gc = lds_f4(a_box + 16u * (unsigned)j);   // broadcast
 #pragma unroll
       for (int u = 0; u < kArmPer; ++u) {
         // positive intersection <=> min(a.max, g.max) > max(a.min, g.min) on both axes (both boxes
@@ -94,7 +99,7 @@ arm_jaccard_bigger_kernel(const __grid_constant__ Layout L, const __grid_constan
           const float h = __fsub_rn(fminf(a[u].z, gc.z), fmaxf(a[u].x, gc.x));
           const float w = __fsub_rn(fminf(a[u].w, gc.w), fmaxf(a[u].y, gc.y));
           const float inter = __fmul_rn(h, w);
-          const float uni = __fadd_rn(__fsub_rn(vol_a[u], inter), s_area[j]);
+          const float uni = __fadd_rn(__fsub_rn(vol_a[u], inter), lds_f1(a_area + 4u * (unsigned)j));
           const float jac = __fdiv_rn(inter, uni);
           if (jac > best[u]) { best[u] = jac; bi[u] = j; }
         }

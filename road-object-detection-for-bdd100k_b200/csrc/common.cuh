@@ -114,6 +114,18 @@ struct Thresholds {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ld.shared on a 32-bit shared-window address
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 // layer of flat anchor n (< n_total).  to_layout() pads offset[i] = n_total for i > n_layers, so the
 // unused entries never count.
 __device__ __forceinline__ int layer_of(const Layout& L, int n) {

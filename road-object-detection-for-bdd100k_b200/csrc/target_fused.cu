@@ -23,18 +23,8 @@ namespace rod {
 
 constexpr int kTfBlock = 128;
 
-// ld.shared with a 32-bit shared-window address computed once per CTA: through a generic pointer the compiler
-// re-derives the window base (S2UR SR_CgaCtaId + 3 uniform ops) in every iteration of the GT walk
-__device__ __forceinline__ float4 lds4(unsigned addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float lds1(unsigned addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
+// (the GT walk reads shared memory through lds_f4 / lds_f1 on a 32-bit window address kept in an opaque register:
+// through a generic pointer ptxas re-derives the window base — S2UR SR_CgaCtaId + 3 uniform ops — in every iteration)
 
 struct FusedParams {
   Layout L;
@@ -112,20 +102,20 @@ target_fused_kernel(const __grid_constant__ FusedParams P) {
       const int g = base + lane;
       bool hit = false;
       if (g < count) {
-        const float4 gc = lds4(a_box + 16u * (unsigned)g);
+        const float4 gc = lds_f4(a_box + 16u * (unsigned)g);
         hit = (gc.z > t_ymin) && (gc.x < t_ymax) && (gc.w > t_xmin) && (gc.y < t_xmax);
       }
       unsigned m = __ballot_sync(0xffffffffu, hit);
       while (m) {                                           // ascending GT index
         const int j = base + __ffs(m) - 1;
         m &= m - 1;
-        const float4 gc = lds4(a_box + 16u * (unsigned)j);  // broadcast
+        const float4 gc = lds_f4(a_box + 16u * (unsigned)j);  // broadcast
         // positive intersection <=> both extents > 0 (x - y > 0 <=> x > y in IEEE arithmetic without FTZ)
         const float h = __fsub_rn(fminf(a.z, gc.z), fmaxf(a.x, gc.x));
         const float w = __fsub_rn(fminf(a.w, gc.w), fmaxf(a.y, gc.y));
         if (h > 0.f && w > 0.f) {
           const float inter = __fmul_rn(h, w);
-          const float uni = __fadd_rn(__fsub_rn(vol_a, inter), lds1(a_area + 4u * (unsigned)j));
+          const float uni = __fadd_rn(__fsub_rn(vol_a, inter), lds_f1(a_area + 4u * (unsigned)j));
           const float jac = __fdiv_rn(inter, uni);
           if (jac > best) { best = jac; bi = j; }
         }
