@@ -483,11 +483,11 @@ def bench_match(G, table, B, extras):
     res["roofline"] = {
         "bound": "hbm" if alg / (hbm * 1e9) >= pair_flops / (fp32_tops * 1e12) else "fp32_nofma",
         "kernel": "target_fused_kernel", "achieved": alg / t_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": frac_hbm,
-        "traffic": measured_traffic("target_fused_kernel"), "traffic_note": "ncu DRAM bytes stop at kernel end: the 80 MB of streaming stores are mostly still dirty in L2 (profiles/r02_traffic.json)",
+        "traffic": measured_traffic("target_fused_kernel"), "traffic_note": "ncu DRAM bytes end with the kernel: most of the 80 MB of stores are still dirty in L2",
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "moved_bytes_per_launch": real,
         "launch_ms": t1["ms_per_step"], "frac_fp32_nofma": frac_fp32, "fp32_nofma_tops_measured": fp32_tops,
         "pair_flops_per_launch": pair_flops,
-        "note": "1 launch = 1 step; algorithmic = SURVEY 8d M (124N+20G B/img), moved = 84N+20G; FP32 no-FMA pair bound (14NG flops) beside it"}
+        "note": "1 launch = 1 step; algorithmic = SURVEY 8d M (124N+20G B/img), moved = 84N+20G; FP32 pair bound = 14NG flops, no FMA"}
     if extras:
         t4 = G.time_loops(runner(fused, args.streams), K)
         t2 = G.time_loops(runner(two_call), K)
@@ -498,8 +498,7 @@ def bench_match(G, table, B, extras):
     res["e2e"] = e2e_match(G, table, B, sets[0], extras)
     res["config"] = {"workload": workload_name("match_encode"), "batch_per_gpu": B, "global_batch": B * G.world,
                      "image": "512x512", "anchors": N, "max_gt": 100, "mean_gt": mean_g,
-                     "api": "net_tools.target_gen (fused ARM+ODM kernel)",
-                     "l2": "inputs > L2: %d rotating sets of ~100 MB" % n_sets,
+                     "api": "net_tools.target_gen (fused ARM+ODM)", "l2": "inputs > L2: %d rotating sets of ~100 MB" % n_sets,
                      "launch": "python launches" if args.no_graphs else "CUDA graph of %d serial steps, one batch in flight" % K,
                      "parallelism": "image-sharded, no collective"}
     return res
@@ -567,7 +566,7 @@ def e2e_match(G, table, B, s0, extras):
     res = {"value": G.world * B / (t["ms_per_step"] * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": t["ms_per_step"],
            "h2d_GBps_per_rank": h2d / (t["ms_per_step"] * 1e-3) / 1e9, "d2h_GBps_per_rank": d2h / (t["ms_per_step"] * 1e-3) / 1e9,
-           "api": "target_gen from pinned host inputs (1 H2D copy), all 8 output lists read back (1 D2H copy), 2 batches in flight"}
+           "api": "target_gen: pinned host inputs (1 H2D copy), all 8 output lists read back (1 D2H copy), 2 batches in flight"}
     if extras:
         mask = make_step(False)
         t2 = G.time_loops(lambda: run(mask, K), K, min_ms=40.0, warm_loops=1, max_loops=20)
