@@ -329,18 +329,30 @@ scan_kernel(const __grid_constant__ ScanParams P) {
   unsigned phases = 0;                                 // bit q = parity of barrier q
   const int b = P.b0 + blockIdx.y, chunk_id = blockIdx.x;   // grid = (chunks per image, images)
   if (tid < C) { S.cnt[tid] = 0u; S.cnt2[tid] = 0u; S.spill_full[tid] = 0u; S.lo_over[tid] = 0u; }
-  // per-class cuts from the sampled histogram: the highest coarse bin t with count(bins >= t) >= target
-  for (int c = tid >> 5; c < C; c += kScanBlock / 32) {
-    const int lane = tid & 31;
-    const unsigned* h = P.g_shist + ((size_t)c * P.batch + b) * kSampleBins + lane * 8;
-    unsigned v[8], sum = 0;
+  // per-class cuts from the sampled histogram: the highest coarse bin t with count(bins >= t) >= target.
+  // One HALF warp per class (16 lanes x 16 bins, four 16-byte loads each): all C <= 16 classes in one round of
+  // loads instead of two rounds of whole warps — this prologue sits in front of every CTA's first compare.
+  static_assert(C <= kScanBlock / 16 && kSampleBins == 256, "one half warp per class, 16 bins per lane");
+  {
+    const int c = tid >> 4, hl = tid & 15;
+    unsigned v[16], sum = 0;
+    if (c < C) {
+      const uint4* h = reinterpret_cast<const uint4*>(P.g_shist + ((size_t)c * P.batch + b) * kSampleBins + hl * 16);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { v[q] = h[q]; sum += v[q]; }
-    unsigned suf = sum;                                // inclusive suffix over lanes (lane 31 owns the top bins)
+      for (int q = 0; q < 4; ++q) {
+        const uint4 x = h[q];
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        sum += x.x + x.y + x.z + x.w;
+      }
+    } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned x = __shfl_down_sync(0xffffffffu, suf, o);
-      if (lane + o < 32) suf += x;
+      for (int q = 0; q < 16; ++q) v[q] = 0u;
+    }
+    unsigned suf = sum;                                // inclusive suffix over the half warp (lane 15 owns the top bins)
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const unsigned x = __shfl_down_sync(0xffffffffu, suf, o, 16);
+      if (hl + o < 16) suf += x;
     }
     const unsigned above = suf - sum;
     int tb[2];
@@ -351,16 +363,16 @@ scan_kernel(const __grid_constant__ ScanParams P) {
       if (above < target && suf >= target) {           // exactly one lane when the row holds >= target samples
         unsigned acc = above;
 #pragma unroll
-        for (int q = 7; q >= 0; --q) {
+        for (int q = 15; q >= 0; --q) {
           acc += v[q];
-          if (acc >= target) { t = lane * 8 + q; break; }
+          if (acc >= target) { t = hl * 16 + q; break; }
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+      for (int o = 8; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o, 16));
       tb[which] = t;
     }
-    if (lane == 0) {
+    if (hl == 0 && c < C) {
       // score_bin(s) >= 4t  <=>  s >= 4t / 1024
       const float hi = fmaxf(P.thr, (float)(4 * tb[0]) * (1.f / (float)kBins));
       const float lo = fmaxf(P.thr, (float)(4 * tb[1]) * (1.f / (float)kBins));
