@@ -371,7 +371,8 @@ int rod_gt_boxes_update(const float* bboxes, const void* labels, int labels_i64,
  *   rod_gt_gather        : DEVICE arrays (the ones above, uploaded once) + indices[batch] (record per
  *                          image; NULL = 0..batch-1) -> bboxes[batch][gmax][4] corner form
  *                          (ymin,xmin,ymax,xmax), labels[batch][gmax], difficults[batch][gmax] (may be
- *                          NULL), counts[batch] = min(#objects, gmax); rows zero padded.  This is the
+ *                          NULL), counts[batch] = min(#objects, gmax); rows zero padded.  An index
+ *                          outside [0, n_records) gives a zero row and counts = -1.  This is the
  *                          input form of rod_gt_boxes_update / rod_corner_to_center / rod_arm_match_encode. */
 int rod_tfrecord_index(const void* data, size_t n_bytes, int verify_crc, int64_t* n_records,
                        int64_t* n_objects);
@@ -381,8 +382,8 @@ int rod_tfrecord_read_gt(const void* data, size_t n_bytes, int verify_crc, int64
                          int64_t* shape);
 int rod_gt_gather(const float* ymin, const float* xmin, const float* ymax, const float* xmax,
                   const int64_t* label, const int64_t* difficult, const int64_t* offsets,
-                  const int64_t* indices, int batch, int gmax, float* bboxes, int64_t* labels,
-                  int64_t* difficults, int32_t* counts, void* stream);
+                  const int64_t* indices, int64_t n_records, int batch, int gmax, float* bboxes,
+                  int64_t* labels, int64_t* difficults, int32_t* counts, void* stream);
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------
  * rod_peak_fp32_nofma: runs a dependent-chain FADD/FMUL (no FMA) kernel and returns in

@@ -88,7 +88,7 @@ SIGNATURES = {
     "rod_clf_loss_grad": (_i, [_LP, _YP, _YP, _YP, _YP, _i, _i, _f, _vp, _vp, _vp]),
     "rod_tfrecord_index": (_i, [_vp, _sz, _i, _vp, _vp]),
     "rod_tfrecord_read_gt": (_i, [_vp, _sz, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "rod_gt_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rod_gt_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rod_gt_boxes_update": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

@@ -19,20 +19,24 @@
 namespace rod {
 
 // ------------------------------------------------------------------------------------------- CRC-32C
-static uint32_t g_crc_table[256];
-static bool g_crc_ready = false;
-static void crc_init() {
-  if (g_crc_ready) return;
-  for (uint32_t i = 0; i < 256; ++i) {
-    uint32_t c = i;
-    for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
-    g_crc_table[i] = c;
+struct CrcTable {
+  uint32_t t[256];
+  CrcTable() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      t[i] = c;
+    }
   }
-  g_crc_ready = true;
+};
+static const uint32_t* crc_table() {
+  static const CrcTable table;                    // (thread-safe initialisation)
+  return table.t;
 }
 static uint32_t masked_crc32c(const unsigned char* p, size_t n) {
+  const uint32_t* table = crc_table();
   uint32_t c = 0xFFFFFFFFu;
-  for (size_t i = 0; i < n; ++i) c = g_crc_table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+  for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
   c ^= 0xFFFFFFFFu;
   return ((c >> 15) | (c << 17)) + 0xa282ead8u;
 }
@@ -185,6 +189,7 @@ static int64_t parse_example(const unsigned char* p, size_t n, int64_t at, int64
   if (!ex.ok) return -1;
   // VarLenFeature: an absent key is an empty list; the four coordinate lists and the labels must agree
   const int64_t g = cnt[K_YMIN] < 0 ? 0 : cnt[K_YMIN];
+  if (g > out.cap - at) return -1;                 // more objects than the caller's arrays hold
   for (int k = K_XMIN; k <= K_LABEL; ++k)
     if ((cnt[k] < 0 ? 0 : cnt[k]) != g) return -2;
   for (int k = K_DIFFICULT; k <= K_TRUNCATED; ++k) {
@@ -198,7 +203,6 @@ static int64_t parse_example(const unsigned char* p, size_t n, int64_t at, int64
 
 static int walk_records(const void* data, size_t n_bytes, int verify_crc, const GtOut& out, int64_t max_records,
                         int64_t* offsets, int64_t* n_records, int64_t* n_objects) {
-  crc_init();
   const unsigned char* p = static_cast<const unsigned char*>(data);
   size_t pos = 0;
   int64_t rec = 0, obj = 0;
@@ -229,18 +233,20 @@ static int walk_records(const void* data, size_t n_bytes, int verify_crc, const 
 }
 
 // ------------------------------------------------------------------------------------------- device gather
-// one warp per image of the batch: record indices[b] -> rows of the padded batch, zero padded, counts clipped to gmax
+// one warp per image of the batch: record indices[b] -> rows of the padded batch, zero padded, counts clipped to gmax;
+// an index outside [0, n_records) gives an all-zero row and counts[b] = -1 (the caller may check without a round trip per step)
 __global__ void __launch_bounds__(256)
 gt_gather_kernel(const float* __restrict__ ymin, const float* __restrict__ xmin, const float* __restrict__ ymax,
                  const float* __restrict__ xmax, const long long* __restrict__ label, const long long* __restrict__ difficult,
-                 const long long* __restrict__ offsets, const long long* __restrict__ indices, int batch, int gmax,
-                 float* __restrict__ bboxes, long long* __restrict__ labels, long long* __restrict__ difficults,
+                 const long long* __restrict__ offsets, const long long* __restrict__ indices, long long n_records, int batch,
+                 int gmax, float* __restrict__ bboxes, long long* __restrict__ labels, long long* __restrict__ difficults,
                  int32_t* __restrict__ counts) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= batch) return;
   const long long rec = indices ? indices[b] : b;
-  const long long o0 = offsets[rec];
-  const int g = (int)min((long long)gmax, offsets[rec + 1] - o0);
+  const bool bad = rec < 0 || rec >= n_records;
+  const long long o0 = bad ? 0 : offsets[rec];
+  const int g = bad ? 0 : (int)min((long long)gmax, offsets[rec + 1] - o0);
   for (int i = lane; i < gmax; i += 32) {
     const bool in = i < g;
     const float4 box = in ? make_float4(ymin[o0 + i], xmin[o0 + i], ymax[o0 + i], xmax[o0 + i]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -248,7 +254,7 @@ gt_gather_kernel(const float* __restrict__ ymin, const float* __restrict__ xmin,
     labels[(long long)b * gmax + i] = in ? label[o0 + i] : 0;
     if (difficults) difficults[(long long)b * gmax + i] = (in && difficult) ? difficult[o0 + i] : 0;
   }
-  if (lane == 0) counts[b] = g;
+  if (lane == 0) counts[b] = bad ? -1 : g;
 }
 
 }  // namespace rod
@@ -282,15 +288,18 @@ extern "C" int rod_tfrecord_read_gt(const void* data, size_t n_bytes, int verify
 }
 
 extern "C" int rod_gt_gather(const float* ymin, const float* xmin, const float* ymax, const float* xmax, const int64_t* label,
-                             const int64_t* difficult, const int64_t* offsets, const int64_t* indices, int batch, int gmax,
-                             float* bboxes, int64_t* labels, int64_t* difficults, int32_t* counts, void* stream) {
+                             const int64_t* difficult, const int64_t* offsets, const int64_t* indices, int64_t n_records,
+                             int batch, int gmax, float* bboxes, int64_t* labels, int64_t* difficults, int32_t* counts, void* stream) {
   using namespace rod;
   ROD_REQUIRE(offsets && bboxes && labels && counts, "rod_gt_gather: NULL pointer argument");
-  ROD_REQUIRE(batch >= 0 && gmax >= 1, "rod_gt_gather: batch=%d gmax=%d invalid", batch, gmax);
+  ROD_REQUIRE(batch >= 0 && gmax >= 1 && n_records >= 0, "rod_gt_gather: batch=%d gmax=%d n_records=%lld invalid", batch, gmax,
+              (long long)n_records);
+  ROD_REQUIRE(indices != nullptr || batch <= n_records, "rod_gt_gather: batch=%d exceeds the %lld records", batch, (long long)n_records);
   if (batch == 0) return ROD_OK;
   gt_gather_kernel<<<(batch + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       ymin, xmin, ymax, xmax, reinterpret_cast<const long long*>(label), reinterpret_cast<const long long*>(difficult),
-      reinterpret_cast<const long long*>(offsets), reinterpret_cast<const long long*>(indices), batch, gmax, bboxes,
+      reinterpret_cast<const long long*>(offsets), reinterpret_cast<const long long*>(indices), (long long)n_records, batch, gmax,
+      bboxes,
       reinterpret_cast<long long*>(labels), reinterpret_cast<long long*>(difficults), counts);
   ROD_LAUNCH_CHECK("gt_gather_kernel");
   return ROD_OK;

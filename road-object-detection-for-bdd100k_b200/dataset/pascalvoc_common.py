@@ -16,6 +16,8 @@ Image bytes ('image/encoded') are skipped: JPEG decoding and augmentation are ou
 from __future__ import annotations
 
 import ctypes
+import mmap
+import os
 
 import numpy as np
 import torch
@@ -55,15 +57,22 @@ class GroundTruth:
 
     def batch(self, indices=None, max_gt=None, batch=None):
         """Padded batch on the device: (bboxes [B,G,4] float32 corner form, labels [B,G] int64, difficults [B,G] int64,
-        counts [B] int32).  `indices`: int64 tensor / sequence of record numbers (None: records 0..batch-1);
+        counts [B] int32).  `indices`: sequence / tensor of record numbers (None: records 0..batch-1; host-side indices are
+        range-checked here, a CUDA tensor is used as it is and marks invalid entries with counts = -1);
         G = max_gt (default: the largest object count of the dataset); rows are zero padded, counts clipped to G."""
         if not isinstance(self.offsets, torch.Tensor) or not self.offsets.is_cuda:
             raise ValueError("call .to('cuda') first: batches are assembled on the device (there is no CPU path)")
         dev = self.offsets.device
         if indices is not None:
-            idx = torch.as_tensor(indices, dtype=torch.int64, device=dev).contiguous()
-            if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= len(self)):
-                raise IndexError("record index out of range")
+            if isinstance(indices, torch.Tensor) and indices.is_cuda:
+                # device-resident indices are not read back (no round trip per step): an index outside the dataset
+                # gives an all-zero row with counts = -1
+                idx = indices.to(device=dev, dtype=torch.int64).contiguous()
+            else:
+                host = np.asarray(indices.cpu() if isinstance(indices, torch.Tensor) else indices, dtype=np.int64).reshape(-1)
+                if host.size and (int(host.min()) < 0 or int(host.max()) >= len(self)):
+                    raise IndexError("record index out of range")
+                idx = torch.from_numpy(host).to(dev)
             B = int(idx.numel())
         else:
             idx, B = None, len(self) if batch is None else int(batch)
@@ -77,7 +86,7 @@ class GroundTruth:
         P = lambda t: t.data_ptr() if t is not None and t.numel() else None
         with _abi.device_guard(dev):
             _abi.check(_abi.lib.rod_gt_gather(P(self.ymin), P(self.xmin), P(self.ymax), P(self.xmax), P(self.label),
-                                              P(self.difficult), self.offsets.data_ptr(), P(idx), B, G, bboxes.data_ptr(),
+                                              P(self.difficult), self.offsets.data_ptr(), P(idx), len(self), B, G, bboxes.data_ptr(),
                                               labels.data_ptr(), diff.data_ptr(), counts.data_ptr(), _abi.stream_ptr(dev)))
         return bboxes, labels, diff, counts
 
@@ -88,23 +97,35 @@ def read_ground_truth(files, verify_crc=True):
     if isinstance(files, (str, bytes, bytearray, memoryview)):
         files = [files]
     parts = []
-    for f in files:
+    for f in files:                             # one file at a time (the records carry the JPEG bytes too): mapped, not copied
         if isinstance(f, str):
-            with open(f, "rb") as fh:
-                parts.append(fh.read())
+            if os.path.getsize(f) == 0:
+                continue
+            with open(f, "rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+                parts.append(_parse(np.frombuffer(mm, dtype=np.uint8), verify_crc))
         else:
-            parts.append(bytes(f))
-    data = b"".join(parts)                      # TFRecord files concatenate
-    buf = ctypes.create_string_buffer(data, len(data)) if data else None
-    ptr = ctypes.addressof(buf) if buf is not None else None
+            parts.append(_parse(np.frombuffer(bytes(f), dtype=np.uint8), verify_crc))
+    if not parts:
+        parts.append(_parse(np.zeros(0, dtype=np.uint8), verify_crc))
+    cat = lambda i: np.concatenate([p[i] for p in parts])
+    offsets, base = [np.zeros(1, dtype=np.int64)], 0
+    for p in parts:                             # TFRecord files concatenate: shift every file's offsets
+        offsets.append(p[7][1:] + base)
+        base += int(p[7][-1])
+    return GroundTruth(cat(0), cat(1), cat(2), cat(3), cat(4), cat(5), cat(6), np.concatenate(offsets), cat(8))
+
+
+def _parse(data, verify_crc):
+    """One file's bytes (uint8 array, may be a read-only mapping) -> the nine arrays of GroundTruth."""
+    ptr = data.ctypes.data if data.size else None
     n_rec, n_obj = ctypes.c_int64(0), ctypes.c_int64(0)
-    _abi.check(_abi.lib.rod_tfrecord_index(ptr, len(data), 1 if verify_crc else 0, ctypes.byref(n_rec), ctypes.byref(n_obj)))
+    _abi.check(_abi.lib.rod_tfrecord_index(ptr, data.size, 1 if verify_crc else 0, ctypes.byref(n_rec), ctypes.byref(n_obj)))
     R, O = n_rec.value, n_obj.value
     f32 = lambda: np.zeros(O, dtype=np.float32)
     i64 = lambda: np.zeros(O, dtype=np.int64)
     ymin, xmin, ymax, xmax, label, difficult, truncated = f32(), f32(), f32(), f32(), i64(), i64(), i64()
     offsets, shape = np.zeros(R + 1, dtype=np.int64), np.zeros((R, 3), dtype=np.int64)
     p = lambda a: a.ctypes.data if a.size else None
-    _abi.check(_abi.lib.rod_tfrecord_read_gt(ptr, len(data), 0, R, O, p(ymin), p(xmin), p(ymax), p(xmax), p(label), p(difficult),
+    _abi.check(_abi.lib.rod_tfrecord_read_gt(ptr, data.size, 0, R, O, p(ymin), p(xmin), p(ymax), p(xmax), p(label), p(difficult),
                                              p(truncated), offsets.ctypes.data, p(shape)))
-    return GroundTruth(ymin, xmin, ymax, xmax, label, difficult, truncated, offsets, shape)
+    return ymin, xmin, ymax, xmax, label, difficult, truncated, offsets, shape

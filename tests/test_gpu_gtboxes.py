@@ -120,6 +120,10 @@ def test_tfrecord_ground_truth_batches_on_device(env):
     assert b2.shape == (3, 4, 4) and c2.tolist() == [min(4, int(z["offsets"][r + 1] - z["offsets"][r])) for r in range(3)]
     with pytest.raises(IndexError):
         dgt.batch([12])
+    # device-resident indices are not read back: an invalid one gives a zero row and counts = -1
+    b3, l3, _, c3 = dgt.batch(torch.tensor([3, 12, -1, 7], device=env.dev))
+    assert c3.tolist() == [int(z["offsets"][4] - z["offsets"][3]), -1, -1, int(z["offsets"][8] - z["offsets"][7])]
+    assert not b3[1:3].any() and not l3[1:3].any() and torch.equal(b3[3], bboxes[0])
     with pytest.raises(ValueError):
         gt.batch([0])                                                   # host arrays: no CPU path
     # into the pipeline: clamp chain -> centre form -> ARM (images without objects give all-zero targets)

@@ -85,3 +85,27 @@ def test_unpacked_encoding_is_accepted():
     head = struct.pack("<Q", len(bad))
     with pytest.raises(ValueError, match="differ in length"):
         _read(head + struct.pack("<I", masked_crc32c(head)) + bad + struct.pack("<I", masked_crc32c(bad)))
+
+
+def test_read_gt_rejects_undersized_arrays():
+    """rod_tfrecord_read_gt called with fewer objects than the file holds must fail before writing past the arrays
+    (the optional difficult / truncated arrays included)."""
+    import ctypes
+    from rodet_b200 import _abi
+    data = np.frombuffer(open(FIXTURE, "rb").read(), dtype=np.uint8)
+    z = golden("voc_gt_expected.npz")
+    R, O = z["offsets"].size - 1, int(z["offsets"][-1])
+    f = lambda n: np.zeros(n, dtype=np.float32)
+    i = lambda n: np.full(n + 8, -7, dtype=np.int64)                    # guard words behind the announced size
+    for announced in (0, 1, O - 1):
+        ymin, xmin, ymax, xmax, label, diff, trunc = f(announced + 8), f(announced + 8), f(announced + 8), f(announced + 8), \
+            i(announced), i(announced), i(announced)
+        offsets = np.zeros(R + 1, dtype=np.int64)
+        rc = _abi.lib.rod_tfrecord_read_gt(data.ctypes.data, data.size, 0, R, announced, ymin.ctypes.data, xmin.ctypes.data,
+                                           ymax.ctypes.data, xmax.ctypes.data, label.ctypes.data, diff.ctypes.data,
+                                           trunc.ctypes.data, offsets.ctypes.data, None)
+        assert rc != 0
+        for a in (label, diff, trunc):
+            assert (a[announced:] == -7).all()
+        with pytest.raises(ValueError):
+            _abi.check(rc)
