@@ -104,13 +104,13 @@ extern "C" int rod_arm_forced_match(const rod_layout_t* layout, const float* anc
   ROD_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 7u) == 0 &&
                   workspace_bytes >= rod_arm_forced_match_workspace_bytes(batch, gmax),
               "rod_arm_forced_match: workspace NULL, misaligned or too small");
+  const size_t smem = (size_t)gmax * 8;
+  ROD_REQUIRE(smem <= 48 * 1024, "rod_arm_forced_match: gmax=%d too large (at most 6144 boxes per image)", gmax);
   if (batch == 0) return ROD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* best = static_cast<unsigned long long*>(workspace);
   gt_best_anchor_kernel<<<dim3(gmax, batch), kFmBlock, 0, st>>>(layout->n_total, anchors_corner, center_bboxes, gt_counts, gmax, best);
   ROD_LAUNCH_CHECK("gt_best_anchor_kernel");
-  const size_t smem = (size_t)gmax * 8;
-  ROD_REQUIRE(smem <= 48 * 1024, "rod_arm_forced_match: gmax=%d too large", gmax);
   if (labels_i64)
     forced_apply_kernel<long long><<<batch, 128, smem, st>>>(layout->n_total, anchors_center, center_bboxes, (const long long*)labels,
                                                              gt_counts, gmax, best, gt, cbboxes, out_labels, pos_mask, match_idx);
