@@ -242,9 +242,16 @@ int rod_bboxes_nms_batch(const float* scores, const float* bboxes, int64_t rows,
  *   out_scores[n_classes][B][keep], out_bboxes[n_classes][B][keep][4],
  *   out_counts[n_classes][B] int32 = number of detections with non-zero score
  *   (may be NULL; this is what the per-rank NCCL count all-gather ships).
- * workspace: rod_detect_workspace_bytes(batch, n_classes, top_k) bytes, 256-aligned. */
+ * workspace: rod_detect_workspace_bytes(batch, n_classes, top_k) bytes, 256-aligned.  For full speed
+ * the rod_detect_workspace_clean_bytes(...) bytes starting at rod_detect_flags_offset(...) should be
+ * zero before the FIRST call with a workspace (n_classes == 11, select_threshold > 0): they hold the
+ * sampled score histogram that steers the candidate cuts, and the library leaves them zero after
+ * every call instead of clearing them in front of every call.  Results never depend on it: stale
+ * contents only send segments to the exact general kernels on that one call. */
 size_t rod_detect_workspace_bytes(const rod_layout_t* layout, int batch, int n_classes,
                                   int top_k);
+size_t rod_detect_workspace_clean_bytes(const rod_layout_t* layout, int batch, int n_classes,
+                                        int top_k);
 /* Diagnostics: byte offset inside the workspace of uint32 flags[n_classes][B] that the last
  * rod_detect / rod_detect_logits call with select_threshold > 0 left behind: non-zero = the segment
  * (class, image) was handed to the exact general kernels (candidate list overflow, sampled score cut

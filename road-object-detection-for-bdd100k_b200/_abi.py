@@ -63,6 +63,7 @@ SIGNATURES = {
     "rod_bboxes_matching_batch": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "rod_detect_workspace_bytes": (_sz, [_LP, _i, _i, _i]),
     "rod_detect_flags_offset": (_sz, [_LP, _i, _i, _i]),
+    "rod_detect_workspace_clean_bytes": (_sz, [_LP, _i, _i, _i]),
     "rod_detect": (_i, [_LP, _vp, _YP, _YP, _YP, _YP, _i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rod_peak_fp32_nofma": (_i, [_i, _vp, _vp, _vp]),
     "rod_l2_flush": (_i, [_vp, _sz, _vp]),

@@ -39,6 +39,7 @@ constexpr int kBins = 1024;
 constexpr int kStreamBlock = 256;
 constexpr int kSegBlock = 256;
 constexpr int kSegWarps = kSegBlock / 32;
+static_assert(kSegBlock == 256, "segment_kernel zeroes its 256-bin sample histogram row with one store per thread");
 
 __device__ __forceinline__ int score_bin(float s) {
   // monotone non-decreasing in s for s > 0; only resolution (never correctness) depends on it
@@ -165,7 +166,8 @@ struct ScanParams {
   int ignore_class, batch, chunk;      // chunk = anchors per CTA (multiple of 256)
   int chunks, spc;                     // CTAs per image, list slots per (class, CTA)
   float thr;
-  unsigned* g_shist;                   // [rows][kSampleBins] histogram of the sampled tiles (sample_kernel)
+  unsigned* g_shist;                   // [rows][kSampleBins] histogram of the sampled tiles (sample_kernel); zero between calls
+  unsigned* g_zero4;                   // [4][rows] + [4]: over flags, dense counters, spill counters, tier-2 flags, any: cleared by sample_kernel
   int target_hi, target_lo;            // sampled candidates that must lie at or above cut_hi / cut_lo
   int* g_est;                          // [rows] cut_lo as a score bin (0: nothing below it was dropped)
   unsigned* g_cnt1;                    // [rows][kMaxChunks] tier-1 candidates written by each CTA
@@ -217,6 +219,13 @@ sample_kernel(const __grid_constant__ ScanParams P) {
   __shared__ float s_rows[8][32 * C];                  // per warp: its 32 sampled rows
   pdl_launch_dependents();                             // the scan pass may start its prologue now
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the flags / counters the LATER kernels of this call raise (this kernel uses none of them): cleared here instead
+  // of by a memset node in front of every call
+  if (blockIdx.x == 0 && threadIdx.x < 4 * C) {
+    const size_t rows = (size_t)C * P.batch;
+    P.g_zero4[(threadIdx.x / C) * rows + (size_t)(threadIdx.x % C) * P.batch + b] = 0u;
+    if (b == 0 && threadIdx.x == 0) P.g_zero4[4 * rows] = 0u;
+  }
   const int n = ((blockIdx.x * 8 + warp) * 32 + lane) * kSampleStride + kSamplePhase;
   const bool valid = n < P.L.n_total;
   const float* row = nullptr;
@@ -524,6 +533,7 @@ struct SegParams {
   long long* dbg;            // optional per-segment phase timestamps (rod_debug_set_timing), else NULL
   unsigned* over;            // out: 1 when the segment must be redone by the exact general kernels
   unsigned* any;             // out: 1 when any segment is
+  unsigned* shist;           // sampled histogram [rows][kSampleBins] of the scan pass (or NULL): every CTA zeroes its row for the next call
   int b0, nb;                // images [b0, b0 + nb) of the batch: one CTA per (class, image of the range)
   int chunks, spc, force_dense;
 };
@@ -597,6 +607,7 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
   if (out_counts && tid == 0) out_counts[r] = 0;       // (flagged rows: the general kernels add theirs)
   if (c == P.ignore_class) return;
   pdl_wait();                                          // candidate lists of the preceding grid complete
+  if (P.shist) P.shist[r * kSampleBins + tid] = 0u;    // (the scan pass has read it; kSampleBins == kSegBlock)
 #define SEG_T(i) do { if (P.dbg != nullptr && tid == 0) P.dbg[r * 8 + (i)] = clock64(); } while (0)
   SEG_T(0);
   // ---- 0. histogram of the segment's listed candidates -> threshold bin (the lowest bin still inside
@@ -977,6 +988,11 @@ static int stream_cap(int k) {
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// bytes at the start of the streaming workspace that hold flags / counters / the sampled histogram
+size_t stream_clean_bytes(int batch, int n_classes) {
+  return (size_t)batch * n_classes * (4 + 4 + 4 + 4 + kSampleBins * 4) + 16;
+}
+
 size_t stream_workspace_bytes(int batch, int n_classes, int top_k) {
   const size_t rows = (size_t)batch * n_classes;
   return align256(rows * (4 + 4 + 4 + 4 + kSampleBins * 4 + kBins * 4) + 16) + align256(rows * 4) + 2 * align256(rows * kMaxChunks * 4) +
@@ -1020,7 +1036,11 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
   p += align256(rows * (size_t)kSpillCap * 8);
   unsigned long long* g_list2 = reinterpret_cast<unsigned long long*>(p);   // [rows][cap]
   int n_chunks = 1, spc = 512;
-  ROD_CUDA(cudaMemsetAsync(g_over, 0, C == 11 ? zero_tma : zero_all, st));
+  // The zero-initialised head: prediction depth 11 with a sample pass keeps it clean itself (sample_kernel clears the
+  // flags of the call, every segment CTA zeroes its histogram row for the next call) — no memset node per call.
+  // The sampled histogram only steers the cuts, so a workspace that was never zeroed costs speed on its first
+  // call (flagged segments go to the exact kernels), never results.
+  bool self_cleaning = false;
   const size_t seg_smem = seg_smem_bytes(cap, top_k, keep);
   ROD_REQUIRE(seg_smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep, seg_smem);
   ROD_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
@@ -1034,7 +1054,7 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     G.nms_thr = nms_thr; G.clip = clip;
     G.cnt2 = g_cnt2; G.over = g_over; G.any = g_any; G.dbg = g_seg_dbg;
     G.list1 = g_list; G.cnt1 = g_cnt1; G.est = g_tbin; G.spill_cnt = g_spill_cnt; G.spill = g_spill;
-    G.list2 = g_list_lo; G.cnt1b = g_cnt1b; G.lo_over = g_lo_over;
+    G.list2 = g_list_lo; G.cnt1b = g_cnt1b; G.lo_over = g_lo_over; G.shist = nullptr;
   };
 
   if (C == 11) {
@@ -1055,6 +1075,9 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     SP.target_lo = (int)(4.0 * top_k * frac + 0.5);
     const bool use_cut = SP.target_hi >= 24 && sampled >= 512;                    // too few samples: never cut
     if (!use_cut) SP.target_hi = SP.target_lo = 0x7fffffff;
+    self_cleaning = use_cut;
+    if (!self_cleaning) ROD_CUDA(cudaMemsetAsync(g_over, 0, zero_tma, st));
+    SP.g_zero4 = g_over;
     int chunks = (4 * sm_count() + batch - 1) / batch;          // one wave of ~4 CTAs per SM (8 per SM measured slower)
     chunks = chunks < 8 ? 8 : (chunks > 32 ? 32 : chunks);     // >= 8: list slices of at most 512 entries
     int chunk = (L.n_total + chunks - 1) / chunks;
@@ -1083,10 +1106,12 @@ int launch_detect_stream(const Layout& L, const float* anchors_center, const Lay
     SegParams G;
     fill_seg_params(G);
     G.chunks = n_chunks; G.spc = spc; G.force_dense = 0;
+    G.shist = self_cleaning ? g_shist : nullptr;
     G.b0 = 0; G.nb = batch;
     ROD_CUDA(launch_pdl(2, segment_kernel, dim3((unsigned)rows), dim3(kSegBlock), seg_smem, st, G, (const unsigned long long*)g_list2,
                         out_scores, out_boxes, out_counts));
   } else {
+    ROD_CUDA(cudaMemsetAsync(g_over, 0, zero_all, st));
     // ---- generic prediction depth: plain-load two-pass kernels, every segment takes the dense route
     StreamParams SP;
     SP.probs = probs; SP.L = L; SP.C = C; SP.ignore_class = ignore_class; SP.batch = batch; SP.thr = select_thr;

@@ -223,6 +223,7 @@ static size_t nms_smem_bytes(int n, int keep, bool dense) {
 int launch_topk_selected(const SelectedScores& src, long long rows, int k, float* out_scores, int32_t* out_idx,
                          cudaStream_t st);
 size_t stream_workspace_bytes(int batch, int n_classes, int top_k);
+size_t stream_clean_bytes(int batch, int n_classes);
 int launch_detect_stream(const Layout& L, const float* anchors_center, const LayeredF& probs, const LayeredF* loc,
                          const LayeredF* refine, const LayeredF* det, int batch, int C, int logits, int ignore_class,
                          float select_thr, float nms_thr, int top_k, int keep, const float* clip, float* out_scores,
@@ -268,6 +269,12 @@ extern "C" size_t rod_detect_flags_offset(const rod_layout_t* layout, int batch,
   if (batch <= 0 || n_classes <= 0 || top_k <= 0) return 0;
   const size_t per = (size_t)batch * n_classes * top_k;
   return ((per * 4 + 255) / 256) * 256 * 2;       // the streaming workspace starts with the flags (launch_detect_stream)
+}
+
+extern "C" size_t rod_detect_workspace_clean_bytes(const rod_layout_t* layout, int batch, int n_classes, int top_k) {
+  (void)layout; (void)top_k;
+  if (batch <= 0 || n_classes <= 0) return 0;
+  return rod::stream_clean_bytes(batch, n_classes);
 }
 
 namespace rod {

@@ -482,8 +482,38 @@ def detect_workspace(anchors_or_n_anchors, batch, top_k, device, num_classes=Non
         lay = table_for(anchors_or_n_anchors, torch.device(device)).layout
     nbytes = int(_abi.lib.rod_detect_workspace_bytes(lay, int(batch), C, int(top_k)))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+    _clean_detect_workspace(ws, int(batch), C, int(top_k))
     ws._rod_key = (int(batch), C, int(top_k))
     return ws
+
+
+_WS_CACHE = {}                                   # (device, stream, batch, C, top_k) -> workspace; a handful of entries
+
+
+def _default_detect_workspace(dev, need, B, C, top_k):
+    """The workspace of calls that pass none: one per (device, stream, geometry), reused (calls on one stream are
+    ordered, so they may share it) — except under CUDA-graph capture, where the buffer must belong to the graph."""
+    if torch.cuda.is_current_stream_capturing():
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+        _clean_detect_workspace(ws, B, C, top_k)
+        return ws
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, B, C, top_k)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < need:
+        if len(_WS_CACHE) >= 8:
+            _WS_CACHE.pop(next(iter(_WS_CACHE)))
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+        _clean_detect_workspace(ws, B, C, top_k)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def _clean_detect_workspace(ws, batch, C, top_k):
+    """Zeroes the bookkeeping head of a detect workspace once (the library keeps it zero between calls: the sampled
+    histogram is cleared by the kernels that consumed it, not by a memset in front of every call)."""
+    off = int(_abi.lib.rod_detect_flags_offset(_abi.Layout(), batch, C, top_k))
+    n = int(_abi.lib.rod_detect_workspace_clean_bytes(_abi.Layout(), batch, C, top_k))
+    ws[off:off + n].zero_()
 
 
 def detect_fallback_flags(workspace):
@@ -522,7 +552,7 @@ def _detect(preds, locs, refine_out, det_out, anchors, select_threshold, nms_thr
         need = int(_abi.lib.rod_detect_workspace_bytes(lay, B, C, top_k))
         ws = workspace
         if ws is None:
-            ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            ws = _default_detect_workspace(dev, need, B, C, int(top_k))
         elif ws.dtype != torch.uint8 or ws.numel() < need or ws.device != dev or not ws.is_contiguous():
             raise ValueError("workspace must be a contiguous uint8 CUDA tensor of >= %d bytes (detect_workspace())" % need)
         clip = None

@@ -346,7 +346,7 @@ def test_detect_unrepresentative_sample(env, where):
 
 
 # ------------------------------------------------------------------------------- bench.py's exact launch geometry
-def _detect_vs_c_oracle(env, layout, probs, ro, do, sthr=0.3, nthr=0.45, topk=400, keep=200):
+def _detect_vs_c_oracle(env, layout, probs, ro, do, sthr=0.3, nthr=0.45, topk=400, keep=200, ws=None, calls=1):
     """decode_detected_bboxes on the whole batch in ONE launch vs the C oracle (oracle/c, pinned bit-for-bit to
     oracle/restated.py by tests/test_oracle_c.py), every image, scores and boxes bit-exact.  Returns
     (#detections, fallback flags [C,B])."""
@@ -355,10 +355,12 @@ def _detect_vs_c_oracle(env, layout, probs, ro, do, sthr=0.3, nthr=0.45, topk=40
     B = probs.shape[0]
     preds = to_cuda_list(probs, table.shapes, (11,), env.dev)
     ro_l, do_l = to_cuda_list(ro, table.shapes, (4,), env.dev), to_cuda_list(do, table.shapes, (4,), env.dev)
-    ws = env.nt.detect_workspace(env.anchors[layout], B, topk, env.dev)
-    rs, rb, counts = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=sthr,
-                                                   nms_threshold=nthr, top_k=topk, keep_top_k=keep, return_counts=True,
-                                                   workspace=ws)
+    if ws is None:
+        ws = env.nt.detect_workspace(env.anchors[layout], B, topk, env.dev)
+    for _ in range(calls):
+        rs, rb, counts = env.nt.decode_detected_bboxes(env.anchors[layout], ro_l, do_l, preds, select_threshold=sthr,
+                                                       nms_threshold=nthr, top_k=topk, keep_top_k=keep, return_counts=True,
+                                                       workspace=ws)
     flags = env.nt.detect_fallback_flags(ws).cpu().numpy()
     o_s, o_b = CP.detected_bboxes(probs, CP.decode_corner(table, ro, do), sthr, nthr, topk, keep)
     ndet = 0
@@ -381,6 +383,24 @@ def test_detect_bench_geometry_bit_exact(env, stress):
     ndet, flags = _detect_vs_c_oracle(env, "512", probs, ro, do)
     assert ndet > 64 * 100
     assert flags[1:].mean() < 0.05, "fallback rate on the i.i.d. bench workload: %.3f" % flags[1:].mean()
+
+
+@pytest.mark.parametrize("fill", ["ones", "random"])
+def test_detect_dirty_workspace_costs_speed_not_results(env, fill):
+    """The library keeps the bookkeeping head of a workspace clean between calls instead of clearing it per call
+    (detect_workspace() zeroes it once).  A workspace that never was — every byte set, or random bytes — must still give
+    the oracle's result on the first call (its sampled histogram is garbage: segments go to the exact kernels), and is
+    clean from the second call on."""
+    probs, ro, do = _detect_inputs(env, "512", 777_000, 4, False)
+    ws = env.nt.detect_workspace(env.anchors["512"], 4, 400, env.dev)
+    if fill == "ones":
+        ws.fill_(0xFF)
+    else:
+        ws.copy_(torch.randint(0, 256, ws.shape, dtype=torch.uint8, device=env.dev, generator=torch.Generator(env.dev).manual_seed(5)))
+    ws._rod_key = (4, 11, 400)
+    _detect_vs_c_oracle(env, "512", probs, ro, do, ws=ws)
+    ndet, flags = _detect_vs_c_oracle(env, "512", probs, ro, do, ws=ws, calls=2)
+    assert ndet > 0 and flags[1:].sum() == 0
 
 
 @pytest.mark.parametrize("mode", ["quadrant", "bumps"])
