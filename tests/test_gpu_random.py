@@ -403,6 +403,49 @@ def test_detect_dirty_workspace_costs_speed_not_results(env, fill):
     assert ndet > 0 and flags[1:].sum() == 0
 
 
+def test_detect_default_workspace_and_graph_capture(env):
+    """Calls without `workspace=` share one cached workspace per (stream, geometry); under CUDA-graph capture the
+    workspace is allocated inside the graph.  Eager calls, repeated calls and graph replays (with the inputs changed in
+    place between replays) all give the same bits as a call with an explicit workspace."""
+    from rodet_b200.utils import net_tools as NT
+    table = env.otable["512"]
+    kw = dict(select_threshold=0.3, nms_threshold=0.45, top_k=400, keep_top_k=200)
+    sets = []
+    for first in (880_000, 881_000):
+        probs, ro, do = _detect_inputs(env, "512", first, 3, False)
+        sets.append((to_cuda_list(probs, table.shapes, (11,), env.dev), to_cuda_list(ro, table.shapes, (4,), env.dev),
+                     to_cuda_list(do, table.shapes, (4,), env.dev)))
+    ref = []
+    for p, r, d in sets:
+        ws = env.nt.detect_workspace(env.anchors["512"], 3, 400, env.dev)
+        ref.append(env.nt.decode_detected_bboxes(env.anchors["512"], r, d, p, workspace=ws, **kw))
+    same = lambda a, b: all(torch.equal(a[0][c].view(torch.int32), b[0][c].view(torch.int32)) and
+                            torch.equal(a[1][c].view(torch.int32), b[1][c].view(torch.int32)) for c in range(1, 11))
+    n_cached = len(NT._WS_CACHE)
+    for _ in range(2):
+        for (p, r, d), want in zip(sets, ref):
+            assert same(env.nt.decode_detected_bboxes(env.anchors["512"], r, d, p, **kw), want)
+    assert len(NT._WS_CACHE) <= n_cached + 1                       # one workspace for the four calls
+    # graph: static input buffers, contents swapped between replays
+    p, r, d = [[t.clone() for t in ts] for ts in sets[0]]
+    side = torch.cuda.Stream(env.dev)
+    side.wait_stream(torch.cuda.current_stream(env.dev))
+    with torch.cuda.stream(side):
+        env.nt.decode_detected_bboxes(env.anchors["512"], r, d, p, **kw)      # warm-up on the capture stream
+    torch.cuda.current_stream(env.dev).wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = env.nt.decode_detected_bboxes(env.anchors["512"], r, d, p, **kw)
+    for rep in range(3):
+        src = sets[rep % 2]
+        for dst_l, src_l in zip((p, r, d), src):
+            for a, b in zip(dst_l, src_l):
+                a.copy_(b)
+        g.replay()
+        torch.cuda.synchronize(env.dev)
+        assert same(out, ref[rep % 2]), "graph replay %d" % rep
+
+
 @pytest.mark.parametrize("mode", ["quadrant", "bumps"])
 @pytest.mark.parametrize("B", [64, 3])
 def test_detect_clustered_scores_bit_exact(env, mode, B):
