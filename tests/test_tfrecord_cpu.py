@@ -109,3 +109,45 @@ def test_read_gt_rejects_undersized_arrays():
             assert (a[announced:] == -7).all()
         with pytest.raises(ValueError):
             _abi.check(rc)
+
+
+def test_mutated_records_never_crash_the_parser():
+    """The reader takes bytes from disk: with the CRC check off, random damage to the protobuf payload (bit flips,
+    truncation, inserted and deleted bytes, oversized varints / lengths) must end in a parsed result or a ValueError —
+    never in an out-of-bounds access (arrays are sized by the index pass and guarded again by the fill pass)."""
+    import struct
+    rng = np.random.default_rng(2024)
+    data = open(FIXTURE, "rb").read()
+    (n0,) = struct.unpack("<Q", data[:8])
+    first = data[12:12 + n0]                                            # payload of record 0
+    from oracle.tf_shim.example_proto import masked_crc32c
+
+    def frame(payload):
+        head = struct.pack("<Q", len(payload))
+        return head + struct.pack("<I", masked_crc32c(head)) + payload + struct.pack("<I", masked_crc32c(payload))
+
+    outcomes = {"ok": 0, "rejected": 0}
+    for trial in range(400):
+        b = bytearray(first)
+        kind = trial % 5
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            del b[int(rng.integers(1, len(b))):]
+        elif kind == 2:
+            at = int(rng.integers(0, len(b)))
+            b[at:at] = bytes(rng.integers(0, 256, int(rng.integers(1, 12)), dtype=np.uint8))
+        elif kind == 3:
+            at = int(rng.integers(0, len(b) - 1))
+            del b[at:at + int(rng.integers(1, 8))]
+        else:
+            at = int(rng.integers(0, len(b)))
+            b[at:at + 1] = b"\xff" * 10 + b"\x7f"                      # an 11-byte varint / absurd length
+        try:
+            gt = _read(frame(bytes(b)) + data, verify_crc=False)         # damaged record in front of the intact file
+            assert len(gt) == 13 and gt.offsets[-1] == gt.label.size == gt.ymin.size
+            outcomes["ok"] += 1
+        except ValueError:
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 50 and outcomes["ok"] > 20, outcomes
