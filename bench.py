@@ -625,8 +625,8 @@ def bench_detect(G, table, B, kind, extras, primary):
     alg = B * (76 * N + (N_CLASSES - 1) * KEEP * 20)
     t_s = t1["ms_per_step"] * 1e-3
     res = {"timing": t1, "ms_per_step": t1["ms_per_step"], "value": G.world * B / t_s, "over_rate": flags,
-           "gpu_launches": 5 * t1["loops"] * K,
-           "kernels_per_step": ["sample_kernel", "scan_kernel", "segment_kernel", "topk_segment_kernel / nms_kernel (flagged segments only)"],
+           "gpu_launches": 4 * t1["loops"] * K,
+           "kernels_per_step": ["sample_kernel", "scan_kernel", "segment_kernel", "nms_kernel (flagged segments only: top-k + NMS)"],
            "detections_per_image": float(stage[0, 1:].sum().item()) / B,
            "roofline": {"bound": "hbm", "kernel": "whole step (sample + scan + segment kernels)", "achieved": alg / t_s / 1e9,
                         "peak": hbm, "unit": "GB/s", "frac": alg / t_s / 1e9 / hbm, "traffic": measured_traffic("decode_nms_step") if kind == "normal" else None,

@@ -46,6 +46,12 @@ struct GatherBoxes {       // fused: candidates come sorted from the top-k kerne
   const unsigned* over_cnt;   // when set: only segments whose streaming list overflowed run here
   const unsigned* over_any;   // when set: non-zero iff any segment is flagged
   unsigned over_cap;
+  // fuse_topk: the CTA first computes the row's top-k itself (topk_row) into scores_w / idx_w (= scores / idx) — the
+  // flagged-segment path of rod_detect, where a separate top-k launch would cost ~1.5 us per call just to find no work
+  int fuse_topk;
+  SelectedScores topk_src;
+  float* scores_w;
+  int32_t* idx_w;
 };
 
 template <bool FUSED>
@@ -75,6 +81,9 @@ nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ Gath
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
   if (FUSED && (int)(r / gsrc.batch) == ignore_class) continue;
   if (FUSED && gsrc.over_cnt != nullptr && gsrc.over_cnt[r] <= gsrc.over_cap) continue;
+  if constexpr (FUSED) {
+    if (gsrc.fuse_topk) topk_row<SelectedScores, kNmsBlock>(gsrc.topk_src, r, n, gsrc.scores_w, gsrc.idx_w, nullptr, nullptr);
+  }
   __syncthreads();
   if (tid == 0) { s_last = 0; s_nsel = 0; }
   __syncthreads();
@@ -83,8 +92,9 @@ nms_kernel(const __grid_constant__ DenseBoxes dsrc, const __grid_constant__ Gath
   if (FUSED) {
     const int b = (int)(r % gsrc.batch);
     for (int j = tid; j < n; j += kNmsBlock) {
-      const float sc = __ldg(gsrc.scores + r * n + j);
-      const int raw = __ldg(gsrc.idx + r * n + j);
+      // (written by this CTA a moment ago when fuse_topk: not through the read-only path)
+      const float sc = gsrc.fuse_topk ? __ldcg(gsrc.scores + r * n + j) : __ldg(gsrc.scores + r * n + j);
+      const int raw = gsrc.fuse_topk ? __ldcg(gsrc.idx + r * n + j) : __ldg(gsrc.idx + r * n + j);
       const bool dummy = raw < 0;
       const int i = raw & 0x7fffffff;
       float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -347,7 +357,9 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   src.over_cnt = over_cnt;
   src.over_any = over_any;
   src.over_cap = (unsigned)over_cap;
-  if ((rc = launch_topk_selected(src, rows, top_k, ws_scores, ws_idx, st))) return rc;
+  // flagged segments of the fast path: the NMS kernel's CTA computes the row's top-k itself (one launch instead of two)
+  const bool fuse_topk = over_cnt != nullptr;
+  if (!fuse_topk && (rc = launch_topk_selected(src, rows, top_k, ws_scores, ws_idx, st))) return rc;
 
   GatherBoxes g;
   g.scores = ws_scores;
@@ -362,6 +374,10 @@ static int detect_impl(const rod_layout_t* layout, const float* anchors_center,
   g.over_cnt = over_cnt;
   g.over_any = over_any;
   g.over_cap = (unsigned)over_cap;
+  g.fuse_topk = fuse_topk ? 1 : 0;
+  g.topk_src = src;
+  g.scores_w = ws_scores;
+  g.idx_w = ws_idx;
   const size_t smem = nms_smem_bytes(top_k, keep_top_k, false);
   ROD_REQUIRE(smem <= 220 * 1024, "rod_detect: top_k=%d keep=%d needs %zu B of shared memory", top_k, keep_top_k, smem);
   auto k = nms_kernel<true>;
