@@ -25,8 +25,8 @@
 //                       rows zero padded.
 // The cuts are a performance device only: a segment whose two tiers together hold fewer than top_k entries
 // although candidates below cut_lo were dropped (a 4x estimation error), whose spill list overflowed, or whose
-// threshold bin holds massive ties, is flagged and redone by the exact general kernels (topk_segment_kernel +
-// nms_kernel), which run only for flagged rows.
+// threshold bin holds massive ties, is flagged and redone by the exact general path (nms_kernel<fused>: top-k by
+// topk_row, then NMS, in one CTA), which runs only for flagged rows.
 // Prediction depths other than 11 use the plain-load two-pass kernels (hist_kernel, thresh_kernel,
 // collect_kernel: full histogram, exact threshold bin) in front of the same segment kernel.
 #include <cuda_fp16.h>
