@@ -972,7 +972,12 @@ segment_kernel(const __grid_constant__ SegParams P, const unsigned long long* __
     }
   }
   SEG_T(5);
-  if (P.dbg != nullptr && tid == 0) { P.dbg[r * 8 + 6] = nk; P.dbg[r * 8 + 7] = cnt; }
+  if (P.dbg != nullptr && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    P.dbg[r * 8 + 6] = nk;
+    P.dbg[r * 8 + 7] = (long long)cnt | ((long long)smid << 32);        // (debug hook: which SM ran the segment)
+  }
 #undef SEG_T
 }
 
