@@ -4,8 +4,6 @@ detect workspace are carved out of a larger allocation filled with a byte patter
 header asks for; after the call the bytes in front of and behind each buffer must be untouched and the
 results must equal those of the public Python API on ordinary allocations.  Geometry: the 512 x 512 layout of
 the bench (TMA scan, sampled cuts, spill lists), small batches, score workloads that fill the list slices."""
-import ctypes
-
 import numpy as np
 import pytest
 import torch
@@ -52,7 +50,8 @@ def ctx(cuda_device):
     ns.abi, ns.synth, ns.nt, ns.dev, ns.config = _abi, synth, net_tools, cuda_device, config
     ns.anchors = golden_anchors("512")
     ns.table = rodet_b200.AnchorTable.from_anchors(ns.anchors, cuda_device)
-    ns.shapes = LAYOUTS["512"][1]
+    ns.shapes = [(fh, fw, 6 if i == 0 else 9) for i, (fh, fw) in enumerate(LAYOUTS["512"][1])]      # (fh, fw, anchors per cell)
+    assert sum(a * b * c for a, b, c in ns.shapes) == ns.table.n
     return ns
 
 
