@@ -29,7 +29,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_w) {
 // sum of n partials by one warp in a fixed order (n is a few hundred: one partial per persistent block)
 __device__ __forceinline__ double warp_sum_partials(const double* p, int n) {
   double t = 0.0;
-  for (int i = threadIdx.x & 31; i < n; i += 32) t += p[i];
+  for (int i = threadIdx.x & 31; i < n; i += 32) t += __ldcg(p + i);          // (written by other blocks of the same kernel in the fused epilogues)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   return t;
@@ -82,15 +82,40 @@ struct ClfState {            // device scalars shared by the kernels of one rod_
   int k_rem;                 // rank still to resolve inside the current prefix
   int n_pos, n_neg_total, n_neg;
   float max_hard_pred;
-  float pad;
+  unsigned ticket;           // blocks of the running kernel that have delivered their partial results (0 between kernels)
   unsigned hist[256];
 };
+
+// "Last block finishes the job": every block calls this after its global writes; exactly one block — the last to
+// arrive — gets true, with the writes of all other blocks visible to loads that bypass L1 (__ldcg).  That block runs
+// the few-thread epilogue (plan, radix pick, final sum) that used to be a <<<1, 32>>> launch of its own, and leaves the
+// ticket at 0 for the next kernel.  No block ever waits for another one.
+__device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned n = gridDim.x * gridDim.y;
+    const bool last = atomicAdd(ticket, 1u) == n - 1u;
+    if (last) *ticket = 0u;
+    s_last = last ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
 
 // per (layer, image): statistics of the IoU map for the IoU factor (:590-600)
 //   z = (iou - mean) / sqrt(var + 1e-8);  z += 0 - min(z);  z /= max(z) + 1e-8;  factor = z^4
 __global__ void __launch_bounds__(kLossBlock)
-iou_stats_kernel(const __grid_constant__ Layout L, const __grid_constant__ LayeredF iou, float4* __restrict__ stats) {
+iou_stats_kernel(const __grid_constant__ Layout L, const __grid_constant__ LayeredF iou, float4* __restrict__ stats,
+                 ClfState* __restrict__ st) {
   __shared__ double s_w[kLossBlock / 32];
+  if (blockIdx.x == 0 && blockIdx.y == 0) {            // first kernel of a rod_clf_loss call: select histogram and ticket start at 0
+    st->hist[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) st->ticket = 0u;
+  }
+  static_assert(kLossBlock == 256, "one histogram bin per thread");
   __shared__ float s_mean, s_min[kLossBlock / 32], s_max[kLossBlock / 32];
   const int l = blockIdx.x, b = blockIdx.y, n = L.offset[l + 1] - L.offset[l];
   const float* p = iou.base[l] + (long long)b * iou.stride[l];
@@ -164,12 +189,81 @@ __device__ __forceinline__ void row_softmax(const float* __restrict__ row, int C
   }
 }
 
+// n_positives, number of negatives to keep (:564, :577-581), radix-select start state.  One warp (of the last block of
+// clf_pass1_kernel); returns the rank to select (= n_neg) in every lane.
+__device__ __forceinline__ int clf_plan(const int* partial_npos, int nparts, long long total, int batch, float negative_ratio,
+                                        ClfState* st) {
+  int c = 0;
+  for (int i = threadIdx.x; i < nparts; i += 32) c += __ldcg(partial_npos + i);
+  c = __reduce_add_sync(0xffffffffu, c);
+  const int max_neg = (int)(total - c);
+  int n_neg = (int)(negative_ratio * (float)c) + batch;                  // tf.cast(3. * n_positives, int32) + bs
+  n_neg = n_neg < max_neg ? n_neg : max_neg;
+  if (threadIdx.x == 0) {
+    st->n_pos = c; st->n_neg_total = max_neg; st->n_neg = n_neg;
+    st->max_hard_pred = 0.f;
+  }
+  return n_neg;
+}
+
+// One warp: given the complete histogram of the current byte among the values matching (prefix, pmask), extend the
+// prefix by the bin that holds the k-th smallest (1-based; k == 0: nothing to select), store the new select state
+// and clear the histogram for the next pass.  lane j owns bins [8j, 8j+8) in ascending order.
+__device__ __forceinline__ void radix_pick(int shift, int k_in, unsigned prefix, unsigned pmask, ClfState* st) {
+  unsigned loc[8], sum = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { loc[q] = __ldcg(&st->hist[8 * threadIdx.x + q]); sum += loc[q]; }
+  unsigned inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned x = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((int)threadIdx.x >= o) inc += x;
+  }
+  const unsigned before = inc - sum;
+  const unsigned k = (unsigned)k_in;
+  const bool own = k >= 1 && before < k && inc >= k;     // at most one lane: the k-th smallest lies in my bins
+  int k_rem = k_in;
+  if (own) {
+    unsigned acc = before;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (acc + loc[q] >= k) {
+        prefix |= (unsigned)(8 * threadIdx.x + q) << shift;
+        pmask |= 255u << shift;
+        k_rem = (int)(k - acc);
+        break;
+      }
+      acc += loc[q];
+    }
+  }
+  const unsigned owners = __ballot_sync(0xffffffffu, own);
+  if (own || (owners == 0u && threadIdx.x == 0)) {       // (no owner — k == 0: the state stays as it was)
+    st->prefix = prefix; st->pmask = pmask; st->k_rem = k_rem;
+    if (shift == 0 && own) st->max_hard_pred = __uint_as_float(prefix);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) st->hist[8 * threadIdx.x + q] = 0u;
+}
+
 // pass 1: per anchor cross entropies and the hard-negative-mining value (:566-575, :602-612)
 __global__ void __launch_bounds__(kLossBlock)
 clf_pass1_kernel(const __grid_constant__ ClfParams P, const float4* __restrict__ stats, float* __restrict__ nvalues,
-                 float* __restrict__ ce0, double* __restrict__ partial_pos, int* __restrict__ partial_npos) {
+                 float* __restrict__ ce0, double* __restrict__ partial_pos, int* __restrict__ partial_npos, float negative_ratio,
+                 ClfState* __restrict__ st) {
   __shared__ double s_w[kLossBlock / 32];
   __shared__ int s_c[kLossBlock / 32];
+  __shared__ unsigned s_h[256];                          // first radix pass (top byte of the nvalues) rides along
+  s_h[threadIdx.x] = 0u;
+  __syncthreads();
+  unsigned cur_bin = 0u, cur_cnt = 0u;                   // run-length in registers: nearly all values share one top byte
+  auto count = [&](float v) {
+    const unsigned bin = __float_as_uint(v) >> 24;
+    if (bin != cur_bin) {
+      if (cur_cnt) atomicAdd(&s_h[cur_bin], cur_cnt);
+      cur_bin = bin; cur_cnt = 0u;
+    }
+    ++cur_cnt;
+  };
   const int tiles_per_image = (P.L.n_total + kLossBlock - 1) / kLossBlock;
   double pos_acc = 0.0;
   int npos = 0;
@@ -188,6 +282,7 @@ clf_pass1_kernel(const __grid_constant__ ClfParams P, const float4* __restrict__
     ce0[o] = __fsub_rn(lse, __fsub_rn(row[0], mx));                       // CE against class 0 (:612)
     if (m_i != 0) {
       nvalues[o] = 1.f;                                                   // tf.where(nmask, p0, 1. - fnmask)
+      count(1.f);
       // CE against the matched class (:605).  A label outside [0, C) gives NaN, like TF's GPU kernel of
       // sparse_softmax_cross_entropy_with_logits (its CPU kernel raises), instead of an out-of-bounds read.
       const float ce = (lab >= 0 && lab < P.C) ? __fsub_rn(lse, __fsub_rn(row[lab], mx)) : __int_as_float(0x7fc00000);
@@ -195,93 +290,53 @@ clf_pass1_kernel(const __grid_constant__ ClfParams P, const float4* __restrict__
       pos_acc += (double)__fmul_rn(ce, f);
       npos += 1;
     } else {
-      nvalues[o] = __fmul_rn(e0, __frcp_rn(s));                           // background probability
+      const float p0 = __fmul_rn(e0, __frcp_rn(s));                       // background probability
+      nvalues[o] = p0;
+      count(p0);
     }
   }
+  if (cur_cnt) atomicAdd(&s_h[cur_bin], cur_cnt);
   const double tot = block_sum(pos_acc, s_w);
   npos = __reduce_add_sync(0xffffffffu, npos);
   if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = npos;
-  __syncthreads();
+  __syncthreads();                                       // (also: every thread's histogram contribution is in s_h)
   if (threadIdx.x == 0) {
     int c = 0;
     for (int w = 0; w < kLossBlock / 32; ++w) c += s_c[w];
     partial_pos[blockIdx.x] = tot;
     partial_npos[blockIdx.x] = c;
   }
-}
-
-// n_positives, number of negatives to keep (:564, :577-581), radix-select start state
-__global__ void __launch_bounds__(32)
-clf_plan_kernel(const int* __restrict__ partial_npos, int nparts, long long total, int batch, float negative_ratio,
-                ClfState* __restrict__ st) {
-  int c = 0;
-  for (int i = threadIdx.x; i < nparts; i += 32) c += partial_npos[i];
-  c = __reduce_add_sync(0xffffffffu, c);
-  for (int i = threadIdx.x; i < 256; i += 32) st->hist[i] = 0u;
-  if (threadIdx.x == 0) {
-    const int max_neg = (int)(total - c);
-    int n_neg = (int)(negative_ratio * (float)c) + batch;                // tf.cast(3. * n_positives, int32) + bs
-    n_neg = n_neg < max_neg ? n_neg : max_neg;
-    st->n_pos = c; st->n_neg_total = max_neg; st->n_neg = n_neg;
-    st->prefix = 0u; st->pmask = 0u; st->k_rem = n_neg;
-    st->max_hard_pred = 0.f;
+  if (s_h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], s_h[threadIdx.x]);
+  if (last_block_arrives(&st->ticket) && threadIdx.x < 32) {
+    const int k = clf_plan(partial_npos, (int)gridDim.x, (long long)P.L.n_total * P.batch, P.batch, negative_ratio, st);
+    radix_pick(24, k, 0u, 0u, st);
   }
 }
 
-// k-th smallest of the nvalues (all >= 0, so the float bits order like unsigned integers):
-// 4 passes of an 8-bit radix histogram + pick
+// k-th smallest of the nvalues (all >= 0, so the float bits order like unsigned integers): 4 passes of an 8-bit radix
+// histogram; the first rides along in clf_pass1_kernel, and the pick after each pass is done by the last block to
+// deliver its counts (last_block_arrives) instead of by a launch of its own.
 __global__ void __launch_bounds__(kLossBlock)
 radix_hist_kernel(const float* __restrict__ v, long long total, int shift, ClfState* __restrict__ st) {
   __shared__ unsigned s_h[256];
   s_h[threadIdx.x] = 0u;
   __syncthreads();
   const unsigned prefix = st->prefix, pmask = st->pmask;
+  const int k = st->k_rem;
   for (long long i = (long long)blockIdx.x * kLossBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kLossBlock) {
     const unsigned key = __float_as_uint(v[i]);
     if ((key & pmask) == prefix) atomicAdd(&s_h[(key >> shift) & 255u], 1u);
   }
   __syncthreads();
   if (s_h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], s_h[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(32)
-radix_pick_kernel(int shift, ClfState* __restrict__ st) {
-  // lane j owns bins [8j, 8j+8) in ascending order
-  unsigned loc[8], sum = 0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { loc[q] = st->hist[8 * threadIdx.x + q]; sum += loc[q]; }
-  unsigned inc = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned x = __shfl_up_sync(0xffffffffu, inc, o);
-    if ((int)threadIdx.x >= o) inc += x;
-  }
-  const unsigned before = inc - sum;
-  const unsigned k = (unsigned)st->k_rem;                // 1-based rank inside the prefix (0: nothing to select)
-  __syncwarp();
-  if (k >= 1 && before < k && inc >= k) {
-    unsigned acc = before;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (acc + loc[q] >= k) {
-        st->prefix |= (unsigned)(8 * threadIdx.x + q) << shift;
-        st->pmask |= 255u << shift;
-        st->k_rem = (int)(k - acc);
-        if (shift == 0) st->max_hard_pred = __uint_as_float(st->prefix);
-        break;
-      }
-      acc += loc[q];
-    }
-  }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 8; ++q) st->hist[8 * threadIdx.x + q] = 0u;
+  if (last_block_arrives(&st->ticket) && threadIdx.x < 32) radix_pick(shift, k, prefix, pmask, st);
 }
 
 // pass 2: sum of the class-0 cross entropy over the mined negatives: nmask & (nvalues < max_hard_pred)  (:585-587, :612-613)
 __global__ void __launch_bounds__(kLossBlock)
 clf_pass2_kernel(const __grid_constant__ ClfParams P, const float* __restrict__ nvalues, const float* __restrict__ ce0,
-                 const ClfState* __restrict__ st, double* __restrict__ partial_neg) {
+                 ClfState* __restrict__ st, const double* __restrict__ partial_pos, double* __restrict__ partial_neg, float inv_bs,
+                 float* __restrict__ out) {
   __shared__ double s_w[kLossBlock / 32];
   const int tiles_per_image = (P.L.n_total + kLossBlock - 1) / kLossBlock;
   const float thr = st->max_hard_pred;
@@ -296,20 +351,18 @@ clf_pass2_kernel(const __grid_constant__ ClfParams P, const float* __restrict__ 
   }
   const double tot = block_sum(acc, s_w);
   if (threadIdx.x == 0) partial_neg[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(32)
-clf_final_kernel(const double* __restrict__ partial_pos, const double* __restrict__ partial_neg, int nparts, float inv_bs,
-                 const ClfState* __restrict__ st, float* __restrict__ out) {
-  const double pos = warp_sum_partials(partial_pos, nparts), neg = warp_sum_partials(partial_neg, nparts);
-  if (threadIdx.x == 0) {
-    const float pos_loss = (float)(pos * (double)inv_bs), neg_loss = (float)(neg * (double)inv_bs);
-    out[0] = __fadd_rn(__fdiv_rn(neg_loss, 2.f), pos_loss);             // clf_loss = neg_loss / 2. + pos_loss  (:615)
-    out[1] = pos_loss;
-    out[2] = neg_loss;
-    out[3] = st->max_hard_pred;
-    out[4] = (float)st->n_pos;
-    out[5] = (float)st->n_neg;
+  // the last block to deliver its partial sums both losses up in the fixed order of the partials (deterministic)
+  if (last_block_arrives(&st->ticket) && threadIdx.x < 32) {
+    const double pos = warp_sum_partials(partial_pos, (int)gridDim.x), neg = warp_sum_partials(partial_neg, (int)gridDim.x);
+    if (threadIdx.x == 0) {
+      const float pos_loss = (float)(pos * (double)inv_bs), neg_loss = (float)(neg * (double)inv_bs);
+      out[0] = __fadd_rn(__fdiv_rn(neg_loss, 2.f), pos_loss);             // clf_loss = neg_loss / 2. + pos_loss  (:615)
+      out[1] = pos_loss;
+      out[2] = neg_loss;
+      out[3] = thr;
+      out[4] = (float)st->n_pos;
+      out[5] = (float)st->n_neg;
+    }
   }
 }
 
@@ -451,24 +504,18 @@ extern "C" int rod_clf_loss(const rod_layout_t* layout, const rod_layered_t* log
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)P.L.n_total * batch;
   const int grid = W.nblk;
-  iou_stats_kernel<<<dim3(P.L.n_layers, batch), kLossBlock, 0, st>>>(P.L, P.iou, W.stats);
+  // six launches: the <<<1, 32>>> plan / pick / final steps run in the last block of the kernel in front of them
+  iou_stats_kernel<<<dim3(P.L.n_layers, batch), kLossBlock, 0, st>>>(P.L, P.iou, W.stats, W.st);
   ROD_LAUNCH_CHECK("iou_stats_kernel");
-  clf_pass1_kernel<<<grid, kLossBlock, 0, st>>>(P, W.stats, W.nvalues, W.ce0, W.ppos, W.pn);
+  clf_pass1_kernel<<<grid, kLossBlock, 0, st>>>(P, W.stats, W.nvalues, W.ce0, W.ppos, W.pn, negative_ratio, W.st);
   ROD_LAUNCH_CHECK("clf_pass1_kernel");
-  clf_plan_kernel<<<1, 32, 0, st>>>(W.pn, grid, total, batch, negative_ratio, W.st);
-  ROD_LAUNCH_CHECK("clf_plan_kernel");
   const unsigned hgrid = (unsigned)std::min<long long>((total + kLossBlock * 8 - 1) / (kLossBlock * 8), 4ll * sm_count());
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    radix_hist_kernel<<<hgrid, kLossBlock, 0, st>>>(W.nvalues, total, shift, W.st);
+  for (int pass = 1; pass < 4; ++pass) {                 // (the top byte was counted by clf_pass1_kernel)
+    radix_hist_kernel<<<hgrid, kLossBlock, 0, st>>>(W.nvalues, total, 24 - 8 * pass, W.st);
     ROD_LAUNCH_CHECK("radix_hist_kernel");
-    radix_pick_kernel<<<1, 32, 0, st>>>(shift, W.st);
-    ROD_LAUNCH_CHECK("radix_pick_kernel");
   }
-  clf_pass2_kernel<<<grid, kLossBlock, 0, st>>>(P, W.nvalues, W.ce0, W.st, W.pneg);
+  clf_pass2_kernel<<<grid, kLossBlock, 0, st>>>(P, W.nvalues, W.ce0, W.st, W.ppos, W.pneg, 1.f / (float)batch, out6);
   ROD_LAUNCH_CHECK("clf_pass2_kernel");
-  clf_final_kernel<<<1, 32, 0, st>>>(W.ppos, W.pneg, grid, 1.f / (float)batch, W.st, out6);
-  ROD_LAUNCH_CHECK("clf_final_kernel");
   return ROD_OK;
 }
 
