@@ -104,7 +104,7 @@ if "detect" in what:
     kw = dict(select_threshold=BN.SELECT_THR, nms_threshold=BN.NMS_THR, top_k=BN.TOP_K, keep_top_k=BN.KEEP, return_counts=True)
     tag = ""
     if True:
-      for name in ("normal", "stress", "quadrant", "bumps"):
+      for name in os.environ.get("ROD_BK_KINDS", "normal,stress,quadrant,bumps").split(","):
         graphs, wss, keep = [], [], []
         for s in range(n_sets):
             first = 500_000 + s * B
